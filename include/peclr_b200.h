@@ -1,0 +1,132 @@
+/* peclr_b200 -- C ABI of the B200-native PeCLR pre-training step (libpeclr_b200.so).
+ *
+ * The reference (dahiyaaneesh/peclr) is pure Python/PyTorch and has no FFI of its own; its boundary
+ * for this path is the Python operator/module API.  These entry points are what
+ * that API binds underneath in this build: each one names the reference code it replaces.  The
+ * ctypes stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; bf16 buffers are passed as void*;
+ * `stream` is a cudaStream_t passed as void* (use torch.cuda.current_stream().cuda_stream); calls are
+ * asynchronous on that stream, never allocate or free, and return 0 on success, a negative code on
+ * error (-1001 bad argument, -1002 driver entry point missing, -1003 tensor-map encoding failed,
+ * -N = cudaError_t N).  Activations are NHWC bf16; convolution weights are bf16 [Cout][kh*kw][Cin]
+ * ("KRSC" = torch.channels_last memory of a (Cout,Cin,kh,kw) tensor); weight gradients are fp32 in
+ * the same layout.  Compiled for sm_100a only; there is no CPU or other-arch fallback.
+ */
+#ifndef PECLR_B200_H_
+#define PECLR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int peclr_abi_version(void);
+
+/* ---- ResNet trunk convolutions: tcgen05/TMEM implicit GEMM fed by TMA (csrc/conv_tc.cu) ------------
+ * Replace nn.Conv2d forward/backward inside ResNetModel.features
+ * (reference src/models/resnet_model.py:16-26,45-52; the 23 shapes of SURVEY.md table A2).
+ * k in {1,3}, stride in {1,2}, padding (k-1)/2, Cin and Cout multiples of 64, H and W even if stride 2.
+ * H, W are always the INPUT spatial size. */
+
+/* y[N,H/s,W/s,Cout] = conv(x[N,H,W,Cin], w[Cout][k*k][Cin]); if stat_sum != NULL also accumulates
+ * per-output-channel sum and sum of squares of the stored bf16 y (training-mode BatchNorm statistics;
+ * the two float[Cout] buffers must be zeroed by the caller). */
+int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
+                       int stride, float* stat_sum, float* stat_sumsq, void* stream);
+/* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,H/s,W/s,Cout], wt[Cin][k*k][Cout]); wt is the transposed
+ * weight copy produced by peclr_weight_transpose.  accumulate != 0 adds into dx (TMA reduce-add). */
+int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
+                       int stride, int accumulate, void* stream);
+/* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x) */
+int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
+                       int stride, void* stream);
+/* 7x7/stride 2/pad 3 stem (features.0).  xpad = [N][H+6][W+16][4] bf16 from peclr_stem_input,
+ * wpack = [64][7][16*4] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
+int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
+                     float* stat_sumsq, void* stream);
+/* dwpack[64][7][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
+int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream);
+
+/* ---- HBM-bound trunk kernels (csrc/bn_act.cu) --------------------------------------------------------
+ * Replace nn.BatchNorm2d(train) + ReLU + residual add, MaxPool2d(3,2,1), AdaptiveAvgPool2d(1) of the
+ * torchvision blocks the reference wraps (resnet_model.py:16-26). */
+
+/* out = [relu]( bn(y) + residual ), bn from the conv epilogue's sums over M rows.  residual is NULL, a
+ * finished activation (rsum == NULL) or a raw conv output with its own BatchNorm (downsample branch).
+ * Saves mean / invstd for backward and updates running stats (momentum, unbiased var) as PyTorch does. */
+int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                   const void* res, const float* rsum, const float* rsumsq, const float* rgamma, const float* rbeta,
+                   void* out, float* mean_out, float* invstd_out, float* running_mean, float* running_var,
+                   float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
+                   float eps, float momentum, int relu, void* stream);
+/* scratch[0:C] = sum g, scratch[C:2C] = sum g*xhat with g = dout * [mask > 0] (mask NULL: g = dout) */
+int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
+                        float* scratch, long long M, int C, void* stream);
+/* dy = gamma*invstd*(g - mean g - xhat*mean(g xhat)); optional g_out = g; dgamma/dbeta += scratch */
+int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
+                       const float* gamma, const float* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
+                       long long M, int C, void* stream);
+/* out[N,H/2,W/2,64] = maxpool3x3s2p1(relu(bn(y[N,H,W,64])))   (features.1-3) */
+int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
+                            const float* beta, void* out, float* mean_out, float* invstd_out, float* running_mean,
+                            float* running_var, int N, int H, int W, float eps, float momentum, void* stream);
+/* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums into scratch[128] */
+int peclr_stem_pool_bwd(const void* dpool, const void* y, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, void* g_out, float* scratch, int N, int H, int W, void* stream);
+int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
+int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream);
+/* cat(transformed_image1, transformed_image2) (hybrid2_model.py:30-32), fp32 NCHW -> padded bf16 NHWC4 */
+int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream);
+
+/* ---- projection head, fp32 (csrc/head.cu); replaces SimCLR.get_projection_head modules
+ * (reference src/models/unsupervised/simclr_model.py:20-35) */
+/* C[m,n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]) */
+int peclr_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, long long sam,
+                long long sak, long long sbk, long long sbn, long long ldc, int accumulate, void* stream);
+int peclr_bn1d_relu_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean_out,
+                        float* invstd_out, float* running_mean, float* running_var, int M, int C, float eps,
+                        float momentum, void* stream);
+int peclr_bn1d_relu_bwd(const float* dout, const float* out, const float* x, const float* mean, const float* invstd,
+                        const float* gamma, float* dx, float* dgamma, float* dbeta, int M, int C, void* stream);
+int peclr_colsum_acc(const float* x, float* out, int M, int N, void* stream);
+
+/* ---- fused equivariance correction + NT-Xent, forward and backward in one launch (csrc/ntxent.cu) ----
+ * Replaces Hybrid2Model.get_transformed_projections after the head + contrastive_step
+ * (hybrid2_model.py:40-90), translate_encodings / rotate_encoding / get_rotation_2D_matrix /
+ * vanila_contrastive_loss (src/models/utils.py:154-186,271-346) and get_projection_stats (:92-106).
+ * p [2B][128] fp32 (view-1 rows then view-2 rows); angle [2B] f64 degrees; jx, jy [2B] int64 pixels;
+ * loss [1]; stats [16] = proj1 {x_mean,x_median,x_min,x_max,y_mean,y_median,y_min,y_max}, proj2 {...};
+ * g_p [2B][128] = dloss/dp (NULL: forward only).  world > 1: the embedding all-gather is fused into
+ * the kernel -- z_peers[r] / flag_peers[r] are rank r's z buffer (the start of its workspace) and flag
+ * array (unsigned[world]) mapped into this process (symmetric / peer memory); epoch must increase by
+ * one per call.  The loss is the GLOBAL-batch mean on every rank and g_p its gradient w.r.t. the local
+ * rows, so parameter gradients are SUMMED across ranks. */
+long long peclr_ntxent_workspace_bytes(int B, int world);
+int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx, const long long* jy, int B, int dim,
+                       int img_h, int img_w, int crop, int rotate, float temperature, float* loss, float* stats,
+                       float* g_p, void* workspace, long long workspace_bytes, int world, int rank,
+                       float* const* z_peers, unsigned* const* flag_peers, unsigned epoch, void* stream);
+
+/* ---- fused LARS-Adam over the flat parameter buffer (csrc/lars_adam.cu); replaces
+ * LARSWrapper(torch.optim.Adam).step() as configured by BaseModel.configure_optimizers
+ * (src/models/base_model.py:57-104).  seg_begin[num_segs+1] are tensor boundaries, seg_wd the weight
+ * decay of each tensor's param group (exclude_from_wt_decay, base_model.py:30-51); chunk_* partition
+ * the buffer into blocks of peclr_opt_chunk_elems() that never straddle a tensor; norms is float[2*num_segs]
+ * scratch.  step is the 1-based Adam step.  p_bf16 (optional) receives the updated weights in bf16. */
+int peclr_opt_chunk_elems(void);
+int peclr_lars_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const long long* seg_begin,
+                         const float* seg_wd, int num_segs, const int* chunk_seg, const long long* chunk_begin,
+                         int num_chunks, float* norms, float lr, int step, float beta1, float beta2, float adam_eps,
+                         int lars, float eta, int clip, float lars_eps, void* stream);
+int peclr_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* table: array of {int64 src_off, int64 dst_off, int32 cout, taps, cin, tile_begin}; one launch
+ * produces every convolution's [Cin][taps][Cout] bf16 dgrad operand from the fp32 master weights */
+int peclr_weight_transpose(const float* src_flat, void* dst_bf16, const void* table, int num_entries, int total_tiles,
+                           void* stream);
+int peclr_stem_pack(const float* w, void* wpack, void* stream);
+int peclr_stem_unpack_grad(const float* gpack, float* g, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PECLR_B200_H_ */

@@ -1,0 +1,102 @@
+"""ctypes binding of libpeclr_b200.so (the C ABI in include/peclr_b200.h).
+
+There is no fallback: if the library is missing or a kernel returns an error the call raises.
+"""
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_longlong, c_uint, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpeclr_b200.so")
+
+P = c_void_p
+I = c_int
+L = c_longlong
+F = c_float
+
+# name -> argtypes (return type is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "peclr_abi_version": [],
+    "peclr_conv2d_fprop": [P, P, P, I, I, I, I, I, I, I, P, P, P],
+    "peclr_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, P],
+    "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P],
+    "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
+    "peclr_stem_wgrad": [P, P, P, I, I, I, P],
+    "peclr_bn_apply": [P] * 19 + [L, I, F, F, I, P],
+    "peclr_bn_bwd_reduce": [P, P, P, P, P, P, L, I, P],
+    "peclr_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, L, I, P],
+    "peclr_stem_bn_relu_pool": [P] * 10 + [I, I, I, F, F, P],
+    "peclr_stem_pool_bwd": [P] * 8 + [I, I, I, P],
+    "peclr_avgpool_fwd": [P, P, I, I, I, P],
+    "peclr_avgpool_bwd": [P, P, I, I, I, P],
+    "peclr_stem_input": [P, P, P, I, I, I, P],
+    "peclr_sgemm": [P, P, P, P, I, I, I, L, L, L, L, L, I, P],
+    "peclr_bn1d_relu_fwd": [P] * 8 + [I, I, F, F, P],
+    "peclr_bn1d_relu_bwd": [P] * 9 + [I, I, P],
+    "peclr_colsum_acc": [P, P, I, I, P],
+    "peclr_ntxent_workspace_bytes": [I, I],
+    "peclr_ntxent_fused": [P, P, P, P, I, I, I, I, I, I, F, P, P, P, P, L, I, I, P, P, c_uint, P],
+    "peclr_opt_chunk_elems": [],
+    "peclr_lars_adam_step": [P, P, P, P, P, P, P, I, P, P, I, P, F, I, F, F, F, I, F, I, F, P],
+    "peclr_cast_bf16": [P, P, L, P],
+    "peclr_weight_transpose": [P, P, P, I, I, P],
+    "peclr_stem_pack": [P, P, P],
+    "peclr_stem_unpack_grad": [P, P, P],
+}
+_RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong}
+_NO_CHECK = {"peclr_abi_version", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems"}
+
+_ERRORS = {-1001: "bad argument", -1002: "CUDA driver entry point unavailable", -1003: "TMA tensor-map encoding failed"}
+
+
+class PeclrKernelError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (raises if it has not been built: run `python -m peclr_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PeclrKernelError(
+            f"{LIB_PATH} is missing: the CUDA extension must be built (python -m peclr_b200.build); "
+            "peclr_b200 has no CPU / PyTorch fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def _check(name, rc):
+    if rc != 0:
+        what = _ERRORS.get(rc, f"cudaError {-rc}" if rc < 0 else "unknown")
+        raise PeclrKernelError(f"{name} failed: {rc} ({what})")
+
+
+def call(name, *args):
+    """Calls an entry point, converting torch tensors to device pointers; raises on a non-zero return."""
+    lib = load()
+    conv = []
+    for a in args:
+        if hasattr(a, "data_ptr"):
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    rc = getattr(lib, name)(*conv)
+    if name in _NO_CHECK:
+        return rc
+    _check(name, rc)
+    return rc
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

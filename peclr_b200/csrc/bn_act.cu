@@ -1,0 +1,540 @@
+// HBM-bound elementwise / reduction kernels of the trunk: training-mode BatchNorm apply (+ residual,
+// + ReLU), BatchNorm backward (reduce + apply), stem max-pool (fused with BN + ReLU) forward/backward,
+// global average pool, and the NCHW fp32 -> padded NHWC4 bf16 input transform.
+//
+// All activation tensors are [M = N*H*W][C] bf16 with C contiguous; every thread owns 8 consecutive
+// channels (one 16-byte vector) and walks rows, so loads/stores are fully coalesced 128-bit accesses
+// and the per-channel BatchNorm coefficients live in registers.  Grids are sized in multiples of the
+// SM count.
+//
+// Replaces ATen/cuDNN BatchNorm2d(train) + ReLU + residual add + MaxPool2d + AdaptiveAvgPool2d of the
+// reference trunk (src/models/resnet_model.py:16-26; torchvision ResNet.forward).
+#include "../../include/peclr_b200.h"
+#include "ptx.cuh"
+
+namespace peclr {
+
+struct alignas(16) bf16x8 {
+  uint32_t v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16_lo(p.v[i]);
+    f[2 * i + 1] = bf16_hi(p.v[i]);
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+
+// mean / inverse std of 8 channels from the sums the convolution epilogue accumulated
+__device__ __forceinline__ void bn_coeffs(const float* sum, const float* sumsq, int c0, float inv_m, float eps,
+                                          float (&mean)[8], float (&invstd)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float m = sum[c0 + i] * inv_m;
+    const float var = fmaxf(sumsq[c0 + i] * inv_m - m * m, 0.f);
+    mean[i] = m;
+    invstd[i] = rsqrtf(var + eps);
+  }
+}
+
+struct BnApplyArgs {
+  const __nv_bfloat16* y;
+  const float *sum, *sumsq, *gamma, *beta;
+  const __nv_bfloat16* res;  // optional second operand of the residual add
+  const float *rsum, *rsumsq, *rgamma, *rbeta;  // if non-null, res is a raw conv output with its own BN
+  __nv_bfloat16* out;
+  float *mean_out, *invstd_out, *running_mean, *running_var;
+  float *rmean_out, *rinvstd_out, *rrunning_mean, *rrunning_var;
+  long long M;
+  int C;
+  float eps, momentum;
+  int relu;
+};
+
+__device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const float (&invstd)[8], int c0, long long M,
+                                               float eps, float momentum, float* mean_out, float* invstd_out,
+                                               float* running_mean, float* running_var) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean_out[c0 + i] = mean[i];
+    invstd_out[c0 + i] = invstd[i];
+    if (running_mean) {
+      const float var = 1.f / (invstd[i] * invstd[i]) - eps;
+      const float unbiased = M > 1 ? var * (float)((double)M / (double)(M - 1)) : var;
+      running_mean[c0 + i] = (1.f - momentum) * running_mean[c0 + i] + momentum * mean[i];
+      running_var[c0 + i] = (1.f - momentum) * running_var[c0 + i] + momentum * unbiased;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  const int tpr = a.C >> 3;  // threads per row
+  const int rows_per_block = 256 / tpr;
+  const int cg = threadIdx.x % tpr;
+  const int roff = threadIdx.x / tpr;
+  if (roff >= rows_per_block) return;
+  const int c0 = cg * 8;
+  const float inv_m = 1.f / (float)a.M;
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(a.sum, a.sumsq, c0, inv_m, a.eps, mean, invstd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    scale[i] = a.gamma[c0 + i] * invstd[i];
+    shift[i] = a.beta[c0 + i] - mean[i] * scale[i];
+  }
+  float rscale[8], rshift[8];
+  const bool res_bn = a.res != nullptr && a.rsum != nullptr;
+  if (res_bn) {
+    float rmean[8], rinvstd[8];
+    bn_coeffs(a.rsum, a.rsumsq, c0, inv_m, a.eps, rmean, rinvstd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rscale[i] = a.rgamma[c0 + i] * rinvstd[i];
+      rshift[i] = a.rbeta[c0 + i] - rmean[i] * rscale[i];
+    }
+    if (blockIdx.x == 0 && roff == 0)
+      bn_bookkeeping(rmean, rinvstd, c0, a.M, a.eps, a.momentum, a.rmean_out, a.rinvstd_out, a.rrunning_mean,
+                     a.rrunning_var);
+  }
+  if (blockIdx.x == 0 && roff == 0)
+    bn_bookkeeping(mean, invstd, c0, a.M, a.eps, a.momentum, a.mean_out, a.invstd_out, a.running_mean, a.running_var);
+
+  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M;
+       r += (long long)gridDim.x * rows_per_block) {
+    const long long off = r * a.C + c0;
+    float v[8];
+    unpack8(ld8(a.y + off), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], scale[i], shift[i]);
+    if (a.res) {
+      float rv[8];
+      unpack8(ld8(a.res + off), rv);
+      if (res_bn) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += fmaf(rv[i], rscale[i], rshift[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += rv[i];
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    st8(a.out + off, pack8(v));
+  }
+}
+
+// ---- BatchNorm backward, pass 1: per-channel sum(g) and sum(g * xhat), g = dout * [mask > 0] -------
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                            const __nv_bfloat16* __restrict__ mask,
+                                                            const __nv_bfloat16* __restrict__ y,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, float* scratch,
+                                                            long long M, int C) {
+  __shared__ float red[2][256][9];
+  const int tpr = C >> 3;
+  const int rows_per_block = 256 / tpr;
+  const int cg = threadIdx.x % tpr;
+  const int roff = threadIdx.x / tpr;
+  const int c0 = cg * 8;
+  float s[8], d[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = d[i] = 0.f, mu[i] = mean[c0 + i], is[i] = invstd[c0 + i];
+  if (roff < rows_per_block) {
+    for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < M;
+         r += (long long)gridDim.x * rows_per_block) {
+      const long long off = r * C + c0;
+      float g[8], yv[8];
+      unpack8(ld8(dout + off), g);
+      unpack8(ld8(y + off), yv);
+      if (mask) {
+        float mv[8];
+        unpack8(ld8(mask + off), mv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = mv[i] > 0.f ? g[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += g[i];
+        d[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], d[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
+  __syncthreads();
+  if (roff == 0) {
+    for (int rr = 1; rr < rows_per_block; ++rr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += red[0][rr * tpr + cg][i], d[i] += red[1][rr * tpr + cg][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red_add_f32(scratch + c0 + i, s[i]);
+      red_add_f32(scratch + C + c0 + i, d[i]);
+    }
+  }
+}
+
+// ---- pass 2: dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)) ----------------------------
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                           const __nv_bfloat16* __restrict__ mask,
+                                                           const __nv_bfloat16* __restrict__ y,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ scratch, __nv_bfloat16* dy,
+                                                           __nv_bfloat16* g_out, float* dgamma, float* dbeta,
+                                                           long long M, int C) {
+  const int tpr = C >> 3;
+  const int rows_per_block = 256 / tpr;
+  const int cg = threadIdx.x % tpr;
+  const int roff = threadIdx.x / tpr;
+  if (roff >= rows_per_block) return;
+  const int c0 = cg * 8;
+  const float inv_m = 1.f / (float)M;
+  float mu[8], is[8], k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+    const float sg = scratch[c0 + i], sgx = scratch[C + c0 + i];
+    k1[i] = gamma[c0 + i] * is[i];
+    k2[i] = sg * inv_m;
+    k3[i] = sgx * inv_m;
+    if (blockIdx.x == 0 && roff == 0) {
+      dbeta[c0 + i] += sg;
+      dgamma[c0 + i] += sgx;
+    }
+  }
+  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < M;
+       r += (long long)gridDim.x * rows_per_block) {
+    const long long off = r * C + c0;
+    float g[8], yv[8];
+    unpack8(ld8(dout + off), g);
+    unpack8(ld8(y + off), yv);
+    if (mask) {
+      float mv[8];
+      unpack8(ld8(mask + off), mv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = mv[i] > 0.f ? g[i] : 0.f;
+    }
+    if (g_out) st8(g_out + off, pack8(g));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (yv[i] - mu[i]) * is[i];
+      g[i] = k1[i] * (g[i] - k2[i] - xh * k3[i]);
+    }
+    st8(dy + off, pack8(g));
+  }
+}
+
+// ---- stem: a = maxpool3x3/s2/p1(relu(bn(y))), y [N][H][W][64] -> a [N][H/2][W/2][64] ----------------
+__global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y,
+                                                                const float* sum, const float* sumsq,
+                                                                const float* gamma, const float* beta,
+                                                                __nv_bfloat16* out, float* mean_out,
+                                                                float* invstd_out, float* running_mean,
+                                                                float* running_var, int N, int H, int W, float eps,
+                                                                float momentum) {
+  const int C = 64, tpr = 8;
+  const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
+  const int c0 = cg * 8;
+  const long long M = (long long)N * H * W;
+  float mean[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(sum, sumsq, c0, 1.f / (float)M, eps, mean, invstd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    scale[i] = gamma[c0 + i] * invstd[i];
+    shift[i] = beta[c0 + i] - mean[i] * scale[i];
+  }
+  if (blockIdx.x == 0 && roff == 0)
+    bn_bookkeeping(mean, invstd, c0, M, eps, momentum, mean_out, invstd_out, running_mean, running_var);
+  const int Ho = H / 2, Wo = W / 2;
+  const long long Mo = (long long)N * Ho * Wo;
+  for (long long r = (long long)blockIdx.x * 32 + roff; r < Mo; r += (long long)gridDim.x * 32) {
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const long long n = r / ((long long)Wo * Ho);
+    float best[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] = 0.f;  // relu output >= 0 and every window has >= 1 valid pixel
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int h = 2 * ho + dh;
+      if (h < 0 || h >= H) continue;
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int w = 2 * wo + dw;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        unpack8(ld8(y + ((n * H + h) * W + w) * C + c0), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], fmaf(v[i], scale[i], shift[i]));
+      }
+    }
+    st8(out + r * C + c0, pack8(best));
+  }
+}
+
+// backward of the above up to (and excluding) the BN-backward apply: g[pixel] = sum over the pooling
+// windows that selected this pixel (first maximum in scan order, as ATen does) of dpool, times relu';
+// also accumulates the BN-backward sums.
+__global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool,
+                                                            const __nv_bfloat16* __restrict__ y,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __nv_bfloat16* g_out,
+                                                            float* scratch, int N, int H, int W) {
+  __shared__ float red[2][256][9];
+  const int C = 64, tpr = 8;
+  const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
+  const int c0 = cg * 8;
+  float mu[8], is[8], scale[8], shift[8], s[8], d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+    scale[i] = gamma[c0 + i] * is[i];
+    shift[i] = beta[c0 + i] - mu[i] * scale[i];
+    s[i] = d[i] = 0.f;
+  }
+  const int Ho = H / 2, Wo = W / 2;
+  const long long M = (long long)N * H * W;
+  for (long long r = (long long)blockIdx.x * 32 + roff; r < M; r += (long long)gridDim.x * 32) {
+    const int w = (int)(r % W);
+    const int h = (int)((r / W) % H);
+    const long long n = r / ((long long)W * H);
+    float yv[8], a[8], g[8];
+    unpack8(ld8(y + r * C + c0), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaxf(fmaf(yv[i], scale[i], shift[i]), 0.f), g[i] = 0.f;
+    // windows (ho, wo) with 2ho-1 <= h <= 2ho+1
+    for (int ho = (h >> 1); ho <= ((h + 1) >> 1); ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = (w >> 1); wo <= ((w + 1) >> 1); ++wo) {
+        if (wo >= Wo) continue;
+        // is (h, w) the first maximum of window (ho, wo)?
+        bool sel[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sel[i] = true;
+        for (int dh = -1; dh <= 1; ++dh) {
+          const int hh = 2 * ho + dh;
+          if (hh < 0 || hh >= H) continue;
+          for (int dw = -1; dw <= 1; ++dw) {
+            const int ww = 2 * wo + dw;
+            if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
+            float ov[8];
+            unpack8(ld8(y + ((n * H + hh) * W + ww) * C + c0), ov);
+            const bool earlier = hh < h || (hh == h && ww < w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float o = fmaxf(fmaf(ov[i], scale[i], shift[i]), 0.f);
+              sel[i] = sel[i] && (earlier ? a[i] > o : a[i] >= o);
+            }
+          }
+        }
+        float dp[8];
+        unpack8(ld8(dpool + ((n * Ho + ho) * Wo + wo) * C + c0), dp);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += sel[i] ? dp[i] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] = a[i] > 0.f ? g[i] : 0.f;
+      s[i] += g[i];
+      d[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], d[i]);
+    }
+    st8(g_out + r * C + c0, pack8(g));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
+  __syncthreads();
+  if (roff == 0) {
+    for (int rr = 1; rr < 32; ++rr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += red[0][rr * tpr + cg][i], d[i] += red[1][rr * tpr + cg][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red_add_f32(scratch + c0 + i, s[i]);
+      red_add_f32(scratch + C + c0 + i, d[i]);
+    }
+  }
+}
+
+// ---- global average pool: x [N][HW][C] bf16 -> out [N][C] fp32 ; and its backward -------------------
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* out, int N,
+                                                          int HW, int C) {
+  const int tpr = C >> 3;
+  const long long total = (long long)N * tpr;
+  const float inv = 1.f / (float)HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % tpr);
+    const long long n = t / tpr;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      float v[8];
+      unpack8(ld8(x + (n * HW + p) * C + cg * 8), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+    float4* o = reinterpret_cast<float4*>(out + n * C + cg * 8);
+    o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* dx, int N,
+                                                          int HW, int C) {
+  const int tpr = C >> 3;
+  const long long total = (long long)N * HW * tpr;
+  const float inv = 1.f / (float)HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % tpr);
+    const long long row = t / tpr;
+    const long long n = row / HW;
+    const float4* g = reinterpret_cast<const float4*>(dout + n * C + cg * 8);
+    const float4 a = g[0], b = g[1];
+    const float v[8] = {a.x * inv, a.y * inv, a.z * inv, a.w * inv, b.x * inv, b.y * inv, b.z * inv, b.w * inv};
+    st8(dx + row * C + cg * 8, pack8(v));
+  }
+}
+
+// ---- input transform: two fp32 NCHW view batches -> one zero-padded bf16 NHWC4 batch -----------------
+// out [2B][H + 6][W + 16][4], image pixel (h, w) at (h + 3, w + 3); channel 3 and the border are zero.
+__global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                         __nv_bfloat16* out, int B, int H, int W) {
+  const int Hp = H + 6, Wp = W + 16;
+  const long long total = (long long)2 * B * Hp * Wp;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(t % Wp);
+    const int hp = (int)((t / Wp) % Hp);
+    const int n = (int)(t / ((long long)Wp * Hp));
+    const int h = hp - 3, w = wp - 3;
+    uint2 v = make_uint2(0u, 0u);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* src = (n < B ? x1 + (long long)n * 3 * H * W : x2 + (long long)(n - B) * 3 * H * W) +
+                         (long long)h * W + w;
+      const long long cs = (long long)H * W;
+      v.x = pack_bf16x2(src[0], src[cs]);
+      v.y = pack_bf16x2(src[2 * cs], 0.f);
+    }
+    *reinterpret_cast<uint2*>(out + t * 4) = v;
+  }
+}
+
+static int grid_for(long long work_items, int per_block) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int last_error() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+}  // namespace peclr
+
+using namespace peclr;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma,
+                              const float* beta, const void* res, const float* rsum, const float* rsumsq,
+                              const float* rgamma, const float* rbeta, void* out, float* mean_out, float* invstd_out,
+                              float* running_mean, float* running_var, float* rmean_out, float* rinvstd_out,
+                              float* rrunning_mean, float* rrunning_var, long long M, int C, float eps, float momentum,
+                              int relu, void* stream) {
+  if (C % 8 || C > 2048 || C < 8 || (256 % (C / 8)) != 0) return -1001;
+  BnApplyArgs a{(const bf16*)y, sum,      sumsq,      gamma,        beta,         (const bf16*)res, rsum,
+                rsumsq,         rgamma,   rbeta,      (bf16*)out,   mean_out,     invstd_out,       running_mean,
+                running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
+                eps,            momentum, relu};
+  const int rows_per_block = 256 / (C / 8);
+  bn_apply_kernel<<<grid_for(M, rows_per_block * 4), 256, 0, (cudaStream_t)stream>>>(a);
+  return last_error();
+}
+
+extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean,
+                                   const float* invstd, float* scratch, long long M, int C, void* stream) {
+  if (C % 8 || C > 2048 || (256 % (C / 8)) != 0) return -1001;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)C * 4, (cudaStream_t)stream);
+  if (e != cudaSuccess) return -(int)e;
+  const int rows_per_block = 256 / (C / 8);
+  bn_bwd_reduce_kernel<<<grid_for(M, rows_per_block * 8), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, scratch, M, C);
+  return last_error();
+}
+
+extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean,
+                                  const float* invstd, const float* gamma, const float* scratch, void* dy,
+                                  void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream) {
+  if (C % 8 || C > 2048 || (256 % (C / 8)) != 0) return -1001;
+  const int rows_per_block = 256 / (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(M, rows_per_block * 4), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, scratch, (bf16*)dy, (bf16*)g_out,
+      dgamma, dbeta, M, C);
+  return last_error();
+}
+
+extern "C" int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
+                                       const float* beta, void* out, float* mean_out, float* invstd_out,
+                                       float* running_mean, float* running_var, int N, int H, int W, float eps,
+                                       float momentum, void* stream) {
+  if ((H & 1) || (W & 1)) return -1001;
+  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2) * (W / 2), 32 * 2), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, mean_out, invstd_out, running_mean, running_var, N, H, W,
+      eps, momentum);
+  return last_error();
+}
+
+extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* y, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, void* g_out, float* scratch, int N, int H,
+                                   int W, void* stream) {
+  if ((H & 1) || (W & 1)) return -1001;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * 64 * 4, (cudaStream_t)stream);
+  if (e != cudaSuccess) return -(int)e;
+  stem_pool_bwd_kernel<<<grid_for((long long)N * H * W, 32 * 4), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dpool, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H, W);
+  return last_error();
+}
+
+extern "C" int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream) {
+  if (C % 8) return -1001;
+  avgpool_fwd_kernel<<<grid_for((long long)N * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, N,
+                                                                                              HW, C);
+  return last_error();
+}
+
+extern "C" int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream) {
+  if (C % 8) return -1001;
+  avgpool_bwd_kernel<<<grid_for((long long)N * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(dout, (bf16*)dx, N,
+                                                                                                   HW, C);
+  return last_error();
+}
+
+extern "C" int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream) {
+  stem_input_kernel<<<grid_for((long long)2 * B * (H + 6) * (W + 16), 256), 256, 0, (cudaStream_t)stream>>>(
+      x1, x2, (bf16*)out, B, H, W);
+  return last_error();
+}

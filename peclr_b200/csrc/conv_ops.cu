@@ -1,0 +1,199 @@
+// Convolution front-ends: turn (N, H, W, Cin, Cout, k, stride) into TMA views + tap tables for the
+// tensor-core kernels in conv_tc.cu.  C ABI declared in include/peclr_b200.h.
+//
+// Replaces, for the ResNet trunk of the reference (src/models/resnet_model.py:16-26, torchvision
+// Bottleneck/BasicBlock convolutions), the cuDNN calls behind nn.Conv2d forward / backward.
+#include "../../include/peclr_b200.h"
+#include "conv_tc.h"
+
+namespace peclr {
+
+static View4 nhwc_view(const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C) {
+  return View4{ptr, C, W, H, N, C, W * C, H * W * C};
+}
+static View4 flat_view(const void* ptr, int64_t M, int64_t C) { return View4{ptr, C, M, 1, 1, C, M * C, M * C}; }
+// pixels (2i + ph, 2j + pw) of an NHWC image as their own (C, W/2, H/2, N) tensor
+static View4 parity_view(const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C, int ph, int pw) {
+  const char* base = static_cast<const char*>(ptr) + ((int64_t)ph * W + pw) * C * 2;
+  return View4{base, C, W / 2, H / 2, N, 2 * C, 2 * W * C, H * W * C};
+}
+
+// Views + taps of the INPUT side of a k x k / stride s convolution with padding (k-1)/2, expressed on
+// the output pixel lattice.  kstride = elements between consecutive taps in the weight matrix.
+static int input_side(const void* x, int N, int H, int W, int C, int k, int stride, int kstride, View4* views,
+                      TapTable* taps, int* num_taps) {
+  memset(taps, 0, sizeof(*taps));
+  if (k != 1 && k != 3) return PECLR_ERR_ARG;
+  if (stride == 1) {
+    views[0] = nhwc_view(x, N, H, W, C);
+    int t = 0;
+    for (int r = 0; r < k; ++r)
+      for (int s = 0; s < k; ++s, ++t) {
+        taps->view[t] = 0;
+        taps->dh[t] = (int8_t)(r - k / 2);
+        taps->dw[t] = (int8_t)(s - k / 2);
+        taps->koff[t] = t * kstride;
+      }
+    *num_taps = t;
+    return 1;
+  }
+  if (stride != 2 || (H & 1) || (W & 1)) return PECLR_ERR_ARG;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) views[ph * 2 + pw] = parity_view(x, N, H, W, C, ph, pw);
+  int t = 0;
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s, ++t) {
+      const int oh = r - k / 2, ow = s - k / 2;  // input pixel = 2 * out + o
+      const int ph = oh & 1, pw = ow & 1;
+      taps->view[t] = (int8_t)(ph * 2 + pw);
+      taps->dh[t] = (int8_t)((oh - ph) / 2);
+      taps->dw[t] = (int8_t)((ow - pw) / 2);
+      taps->koff[t] = t * kstride;
+    }
+  *num_taps = t;
+  return 4;
+}
+
+}  // namespace peclr
+
+using namespace peclr;
+
+extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
+                                  int stride, float* stat_sum, float* stat_sumsq, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cin % 64 || Cout % 64) return PECLR_ERR_ARG;
+  const int Ho = H / stride, Wo = W / stride;
+  TapTable taps;
+  int num_taps = 0;
+  View4 views[kMaxViews];
+  if (k == 1 && stride == 1) {
+    memset(&taps, 0, sizeof(taps));
+    views[0] = flat_view(x, (int64_t)N * H * W, Cin);
+    View4 d = flat_view(y, (int64_t)N * H * W, Cout);
+    return conv_gemm_launch(views, 1, w, Cin, Cout, d, taps, 1, Cin / 64, stat_sum, stat_sumsq, 0, st);
+  }
+  const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
+  if (nv < 0) return nv;
+  View4 d = nhwc_view(y, N, Ho, Wo, Cout);
+  return conv_gemm_launch(views, nv, w, (int64_t)num_taps * Cin, Cout, d, taps, num_taps, Cin / 64, stat_sum,
+                          stat_sumsq, 0, st);
+}
+
+extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                                  int k, int stride, int accumulate, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cin % 64 || Cout % 64 || (k != 1 && k != 3)) return PECLR_ERR_ARG;
+  const int Ho = H / stride, Wo = W / stride;
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  View4 a;
+  const int64_t ktot = (int64_t)k * k * Cout;
+  if (stride == 1) {
+    if (k == 1) {
+      a = flat_view(dy, (int64_t)N * H * W, Cout);
+      View4 d = flat_view(dx, (int64_t)N * H * W, Cin);
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, accumulate, st);
+    }
+    a = nhwc_view(dy, N, H, W, Cout);
+    int t = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s, ++t) {
+        taps.dh[t] = (int8_t)(1 - r);
+        taps.dw[t] = (int8_t)(1 - s);
+        taps.koff[t] = t * Cout;
+      }
+    View4 d = nhwc_view(dx, N, H, W, Cin);
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, nullptr, nullptr, accumulate, st);
+  }
+  if (stride != 2 || (H & 1) || (W & 1)) return PECLR_ERR_ARG;
+  a = nhwc_view(dy, N, Ho, Wo, Cout);
+  if (k == 1) {
+    // only the even/even pixels of dx receive gradient
+    if (!accumulate) {
+      cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, st);
+      if (e != cudaSuccess) return -(int)e;
+    }
+    View4 d = parity_view(dx, N, H, W, Cin, 0, 0);
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, accumulate, st);
+  }
+  // 3x3 stride 2: one launch per parity class of the input pixel; taps r with (ph + 1 - r) even
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int t = 0;
+      for (int r = 0; r < 3; ++r) {
+        if ((ph + 1 - r) & 1) continue;
+        for (int s = 0; s < 3; ++s) {
+          if ((pw + 1 - s) & 1) continue;
+          taps.view[t] = 0;
+          taps.dh[t] = (int8_t)((ph + 1 - r) / 2);
+          taps.dw[t] = (int8_t)((pw + 1 - s) / 2);
+          taps.koff[t] = (r * 3 + s) * Cout;
+          ++t;
+        }
+      }
+      View4 d = parity_view(dx, N, H, W, Cin, ph, pw);
+      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, nullptr, nullptr, accumulate, st);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                                  int k, int stride, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cin % 64 || Cout % 64) return PECLR_ERR_ARG;
+  const int Ho = H / stride, Wo = W / stride;
+  TapTable taps;
+  int num_taps = 0;
+  View4 views[kMaxViews];
+  if (k == 1 && stride == 1) {
+    memset(&taps, 0, sizeof(taps));
+    views[0] = flat_view(x, (int64_t)N * H * W, Cin);
+    View4 d = flat_view(dy, (int64_t)N * H * W, Cout);
+    return conv_wgrad_launch(views, 1, d, taps, 1, Cin, Cout, dw, st);
+  }
+  const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
+  if (nv < 0) return nv;
+  View4 d = nhwc_view(dy, N, Ho, Wo, Cout);
+  return conv_wgrad_launch(views, nv, d, taps, num_taps, Cin, Cout, dw, st);
+}
+
+// ---- 7x7 / stride 2 / pad 3 stem on a zero-padded NHWC4 image ------------------------------------
+// xpad: [N][H + 6][W + 16][4] bf16, pixel (h, w) of the image at (h + 3, w + 3), everything else 0.
+// For output (ho, wo) and filter row r the 16-pixel window starting at padded pixel (2ho + r, 2wo) is
+// 64 contiguous bf16: that window is the "channel" dimension of an ordinary K-major GEMM operand.
+// Weights: [64][7][16 * 4] bf16 (taps s >= 7 and channel 3 are zero), K = 448.
+static void stem_views(const void* xpad, int N, int H, int W, View4* views, TapTable* taps) {
+  const int64_t Hp = H + 6, Wp = W + 16;
+  memset(taps, 0, sizeof(*taps));
+  for (int pr = 0; pr < 2; ++pr) {
+    const char* base = static_cast<const char*>(xpad) + (int64_t)pr * Wp * 4 * 2;
+    views[pr] = View4{base, 64, W / 2, Hp / 2, N, 8, 2 * Wp * 4, Hp * Wp * 4};
+  }
+  for (int r = 0; r < 7; ++r) {
+    taps->view[r] = (int8_t)(r & 1);
+    taps->dh[r] = (int8_t)(r >> 1);
+    taps->dw[r] = 0;
+    taps->koff[r] = r * 64;
+  }
+}
+
+extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
+                                float* stat_sumsq, void* stream) {
+  if ((H & 1) || (W & 1)) return PECLR_ERR_ARG;
+  View4 views[kMaxViews];
+  TapTable taps;
+  stem_views(xpad, N, H, W, views, &taps);
+  View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
+  return conv_gemm_launch(views, 2, wpack, 7 * 64, 64, d, taps, 7, 1, stat_sum, stat_sumsq, 0,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream) {
+  if ((H & 1) || (W & 1)) return PECLR_ERR_ARG;
+  View4 views[kMaxViews];
+  TapTable taps;
+  stem_views(xpad, N, H, W, views, &taps);
+  View4 d = View4{dy, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
+  return conv_wgrad_launch(views, 2, d, taps, 7, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
+}

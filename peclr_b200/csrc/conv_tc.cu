@@ -1,0 +1,591 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// Data layout in HBM: activations NHWC bf16, viewed by TMA as rank-4 tensors (C, W, H, N); weights
+// bf16 [Cout][taps][Cin] ("KRSC", K-major for fprop) and its transpose [Cin][taps][Cout] for dgrad;
+// weight gradients fp32 [Cout][taps][Cin].
+//
+//   conv_gemm_kernel  (fprop / dgrad): D[pix, n] = sum_taps sum_c A[pix + tap, c] * B[n, tap, c]
+//       A tile  = 128 output pixels (a Wb x Hb x Nb box of the pixel lattice) x 64 channels, one TMA box
+//                 per filter tap; out-of-image taps are zero-filled by TMA (that is the padding).
+//       B tile  = BN output channels x 64, K-major.   D = 128 x BN fp32 accumulator in TMEM.
+//       Strided convolutions read/write parity sub-lattices of the image (plain tiled TMA views with
+//       doubled strides), so one kernel covers 1x1, 3x3, stride 1 and 2, fprop and dgrad, and the
+//       7x7 stem (whose "channels" are 16-pixel x 4-channel windows of a padded NHWC4 image).
+//       Epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA store (or TMA reduce-add for
+//       gradient accumulation), plus per-channel sum / sum-of-squares of the stored values for the
+//       following training-mode BatchNorm.
+//
+//   conv_wgrad_kernel : dW[n, tap, c] += sum_pix dY[pix, n] * X[pix + tap, c]
+//       both operands are loaded exactly as above ([pixels][64 channels] boxes) and consumed as
+//       MN-major UMMA operands (contraction over pixels); M = 128 input channels, N = BN output
+//       channels, up to 512/BN taps accumulate side by side in TMEM; split over pixel ranges across
+//       CTAs and reduced with fp32 red.global.add.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
+// epilogue (one TMEM lane quarter each).
+#include "conv_tc.h"
+
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace peclr {
+
+constexpr int kStageA = 128 * 128;  // 128 pixel rows x 64 bf16
+
+struct GemmParams {
+  CUtensorMap a_maps[kMaxViews];
+  CUtensorMap b_map;
+  CUtensorMap d_map;
+  TapTable taps;
+  int num_taps, c_chunks;
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int Wb, Hb, Nb;
+  int cout;
+  float* stat_sum;
+  float* stat_sumsq;
+  int reduce_add;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStageB = BN * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * kStageA;
+  uint8_t* sD = sB + STAGES * kStageB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sD + (BN / 64) * kStageA);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][cout] when stats are requested
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool want_stats = p.stat_sum != nullptr;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < kMaxViews; ++i) prefetch_tmap(&p.a_maps[i]);
+    prefetch_tmap(&p.b_map);
+    prefetch_tmap(&p.d_map);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<2 * BN>(tmem_slot);
+  }
+  if (want_stats && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 128) sStat[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int num_kb = p.num_taps * p.c_chunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.Wb;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const CUtensorMap* amap = &p.a_maps[p.taps.view[tap]];
+          const int cw = w0 + p.taps.dw[tap];
+          const int ch = h0 + p.taps.dh[tap];
+          const int kbase = p.taps.koff[tap];
+          for (int c = 0; c < p.c_chunks; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], kStageA + kStageB);
+            tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
+            tma_load_2d(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64, nt * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * kStageA), 0, 1024);
+          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * kStageB), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the swizzle atom
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int w0 = (mt % p.tiles_w) * p.Wb;
+      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
+      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      if (et == 0) tma_wait_group_read0();  // previous tile's TMA store has finished reading sD
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        uint8_t* box = sD + (chunk >> 1) * kStageA + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c16 = (chunk & 1) * 4 + j;  // 16-byte chunk inside the 128-byte row
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+          v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          *reinterpret_cast<uint4*>(box + ((c16 ^ (row & 7)) << 4)) = v;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) {
+          if (p.reduce_add)
+            tma_reduce_add_4d(&p.d_map, sD + b * kStageA, nt * BN + b * 64, w0, h0, n0);
+          else
+            tma_store_4d(&p.d_map, sD + b * kStageA, nt * BN + b * 64, w0, h0, n0);
+        }
+        tma_commit_group();
+      }
+      if (want_stats) {
+        // column sums of the bf16 values just staged (exactly what the next kernels will read)
+        constexpr int kPairs = BN / 2;
+        constexpr int kRowGroups = 128 / kPairs > 0 ? 128 / kPairs : 1;
+        const int pair = et % kPairs;
+        const int rg = et / kPairs;
+        const int col = pair * 2;
+        const uint8_t* base = sD + (col >> 6) * kStageA + ((col & 7) << 1);
+        const int c16 = (col & 63) >> 3;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (rg < kRowGroups) {
+#pragma unroll 4
+          for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
+            const float a = bf16_lo(v), b = bf16_hi(v);
+            s0 += a;
+            s1 += b;
+            q0 = fmaf(a, a, q0);
+            q1 = fmaf(b, b, q1);
+          }
+          float* ss = sStat + nt * BN + col;
+          atomicAdd(ss, s0);
+          atomicAdd(ss + 1, s1);
+          atomicAdd(ss + p.cout, q0);
+          atomicAdd(ss + p.cout + 1, q1);
+        }
+      }
+    }
+    if (et == 0) tma_wait_group0();
+    if (want_stats) {
+      named_bar_sync(1, 128);
+      for (int i = et; i < p.cout; i += 128) {
+        const float s = sStat[i], qq = sStat[p.cout + i];
+        if (s != 0.f || qq != 0.f) {
+          red_add_f32(p.stat_sum + i, s);
+          red_add_f32(p.stat_sumsq + i, qq);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+struct WgradParams {
+  CUtensorMap x_maps[kMaxViews];
+  CUtensorMap dy_map;
+  TapTable taps;
+  int num_taps, taps_per_unit, tap_groups;
+  int m_tiles, n_tiles, ksplit;
+  int tiles_w, tiles_h, tiles_n;
+  int Wb, Hb, Nb;
+  int cin, a_boxes;
+  int64_t ld_co;  // elements between consecutive output channels in dW ( = taps * cin )
+  float* dw;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+  constexpr int kBBytes = (BN / 64) * kBoxBytes;
+  constexpr int kABytes = 2 * kBoxBytes;  // 128 input channels per tap
+  const int G = p.taps_per_unit;
+  const int stage_bytes = kBBytes + G * kABytes;
+  const int stages = (200 * 1024) / stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + 32;
+  uint64_t* tfull = empty + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < kMaxViews; ++i) prefetch_tmap(&p.x_maps[i]);
+    prefetch_tmap(&p.dy_map);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < stages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (m tile, n tile, tap group, pixel range)
+  int u = blockIdx.x;
+  const int mt = u % p.m_tiles;
+  u /= p.m_tiles;
+  const int nt = u % p.n_tiles;
+  u /= p.n_tiles;
+  const int tg = u % p.tap_groups;
+  const int ks = u / p.tap_groups;
+  const int tap0 = tg * G;
+  const int ntap = min(G, p.num_taps - tap0);
+  const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int per = (total_chunks + p.ksplit - 1) / p.ksplit;
+  const int c_begin = ks * per;
+  const int c_end = min(total_chunks, c_begin + per);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int w0 = (c % p.tiles_w) * p.Wb;
+        const int h0 = ((c / p.tiles_w) % p.tiles_h) * p.Hb;
+        const int n0 = (c / (p.tiles_w * p.tiles_h)) * p.Nb;
+        uint8_t* st = smem + stage * stage_bytes;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], kBBytes + ntap * p.a_boxes * kBoxBytes);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_4d(&p.dy_map, &full[stage], st + b * kBoxBytes, nt * BN + b * 64, w0, h0, n0);
+        for (int g = 0; g < ntap; ++g) {
+          const int tap = tap0 + g;
+          const CUtensorMap* xm = &p.x_maps[p.taps.view[tap]];
+          for (int b = 0; b < p.a_boxes; ++b)
+            tma_load_4d(xm, &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, mt * 128 + b * 64,
+                        w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + stage * stage_bytes);
+        const uint64_t b_desc = make_smem_desc(st, kBoxBytes, 1024);
+        for (int g = 0; g < ntap; ++g) {
+          const uint64_t a_desc = make_smem_desc(st + kBBytes + g * kABytes, kBoxBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels (k rows of 128 B) per UMMA: +2048 B
+            umma_bf16(tmem_base + g * BN, a_desc + 128 * k, b_desc + 128 * k, idesc, (c > c_begin) || (k > 0));
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else if (c_end > c_begin) {
+    const int q = warp & 3;
+    const int ci = mt * 128 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (int g = 0; g < ntap; ++g) {
+      const int tap = tap0 + g;
+      float* out = p.dw + static_cast<int64_t>(tap) * p.cin + ci;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + chunk * 32, r);
+        tmem_ld_wait();
+        if (ci < p.cin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = nt * BN + chunk * 32 + j;
+            red_add_f32(out + co * p.ld_co, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// rank-4 bf16 view (C, W, H, N); strides in elements for W, H, N; box (64, bw, bh, bn); 128B swizzle.
+static int encode_view(CUtensorMap* m, const View4& v, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return PECLR_ERR_DRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "peclr: cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%d,%d,%d)\n",
+            (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+            (unsigned long long)strides[2], bw, bh, bn);
+    return PECLR_ERR_TENSORMAP;
+  }
+  return 0;
+}
+
+static int encode_matrix(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return PECLR_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "peclr: cuTensorMapEncodeTiled(2d) failed: %d cols=%lld rows=%lld\n", (int)r, (long long)cols,
+            (long long)rows);
+    return PECLR_ERR_TENSORMAP;
+  }
+  return 0;
+}
+
+// Chooses the pixel box (bw, bh, bn) with bw*bh*bn == target (a power of two) that needs the fewest tiles.
+void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn) {
+  long best = -1;
+  for (int w = 1; w <= target; w *= 2)
+    for (int h = 1; w * h <= target; h *= 2) {
+      const int n = target / (w * h);
+      if (w > 256 || h > 256 || n > 256) continue;
+      const long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+      // fewer tiles first; then wider boxes (longer contiguous runs)
+      if (best < 0 || tiles < best || (tiles == best && w > *bw)) {
+        best = tiles;
+        *bw = w;
+        *bh = h;
+        *bn = n;
+      }
+    }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)STAGES * (kStageA + BN * 128) + (size_t)(BN / 64) * kStageA + 256 +
+                      (stats ? 2 * (size_t)p.cout * 4 : 0);
+  auto kern = conv_gemm_kernel<BN, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, 192, smem, stream>>>(p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
+                     float* stat_sumsq, int reduce_add, cudaStream_t stream) {
+  if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
+  if (nout % 64 != 0 || ktot % 64 != 0 || d_view.c != nout) return PECLR_ERR_ARG;
+  if (stat_sum && nout > 2048) return PECLR_ERR_ARG;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int bw = 1, bh = 1, bn = 1;
+  choose_box((int)d_view.w, (int)d_view.h, (int)d_view.n, 128, &bw, &bh, &bn);
+  int rc;
+  for (int i = 0; i < kMaxViews; ++i)
+    if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
+  const int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+  if ((rc = encode_matrix(&p.b_map, w, ktot, nout, BN))) return rc;
+  if ((rc = encode_view(&p.d_map, d_view, bw, bh, bn))) return rc;
+  p.taps = taps;
+  p.num_taps = num_taps;
+  p.c_chunks = c_chunks;
+  p.Wb = bw, p.Hb = bh, p.Nb = bn;
+  p.tiles_w = (int)((d_view.w + bw - 1) / bw);
+  p.tiles_h = (int)((d_view.h + bh - 1) / bh);
+  p.tiles_n = (int)((d_view.n + bn - 1) / bn);
+  p.n_tiles = (int)(nout / BN);
+  p.cout = (int)nout;
+  p.stat_sum = stat_sum;
+  p.stat_sumsq = stat_sumsq;
+  p.reduce_add = reduce_add;
+  const bool stats = stat_sum != nullptr;
+  if (BN == 256) return launch_gemm_t<256, 3>(p, stats, stream);
+  if (BN == 128) return launch_gemm_t<128, 4>(p, stats, stream);
+  return launch_gemm_t<64, 6>(p, stats, stream);
+}
+
+template <int BN>
+static int launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
+  const size_t smem = 1024 + 200 * 1024 + 1024;
+  auto kern = conv_wgrad_kernel<BN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  const int grid = p.m_tiles * p.n_tiles * p.tap_groups * p.ksplit;
+  kern<<<grid, 192, smem, stream>>>(p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
+                      int cin, int cout, float* dw, cudaStream_t stream) {
+  if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
+  if (cin % 64 != 0 || cout % 64 != 0 || dy_view.c != cout) return PECLR_ERR_ARG;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int bw = 1, bh = 1, bn = 1;
+  choose_box((int)dy_view.w, (int)dy_view.h, (int)dy_view.n, 64, &bw, &bh, &bn);
+  int rc;
+  for (int i = 0; i < kMaxViews; ++i)
+    if ((rc = encode_view(&p.x_maps[i], x_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
+  if ((rc = encode_view(&p.dy_map, dy_view, bw, bh, bn))) return rc;
+  // multi-tap filters keep several taps' accumulators side by side in TMEM (dY is loaded once per group)
+  const int BN = num_taps > 1 ? (cout % 128 == 0 ? 128 : 64) : (cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64));
+  p.taps = taps;
+  p.num_taps = num_taps;
+  p.taps_per_unit = num_taps == 9 ? 3 : (num_taps < 4 ? num_taps : 4);  // G * BN <= 512 columns, >= 2 smem stages
+  p.tap_groups = (num_taps + p.taps_per_unit - 1) / p.taps_per_unit;
+  p.m_tiles = (cin + 127) / 128;
+  p.n_tiles = cout / BN;
+  p.a_boxes = cin >= 128 ? 2 : 1;
+  p.Wb = bw, p.Hb = bh, p.Nb = bn;
+  p.tiles_w = (int)((dy_view.w + bw - 1) / bw);
+  p.tiles_h = (int)((dy_view.h + bh - 1) / bh);
+  p.tiles_n = (int)((dy_view.n + bn - 1) / bn);
+  const int chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int base_units = p.m_tiles * p.n_tiles * p.tap_groups;
+  int ksplit = (2 * sm_count() + base_units - 1) / base_units;
+  const int max_split = (chunks + 7) / 8;  // at least 8 pixel chunks (512 pixels) per unit
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  p.cin = cin;
+  p.ld_co = (int64_t)num_taps * cin;
+  p.dw = dw;
+  if (BN == 256) return launch_wgrad_t<256>(p, stream);
+  if (BN == 128) return launch_wgrad_t<128>(p, stream);
+  return launch_wgrad_t<64>(p, stream);
+}
+
+}  // namespace peclr

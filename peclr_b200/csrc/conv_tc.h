@@ -1,0 +1,44 @@
+// Internal interface between the tensor-core GEMM kernels (conv_tc.cu) and the convolution
+// front-ends (conv_ops.cu).  Not part of the C ABI (see include/peclr_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#define PECLR_ERR_ARG (-1001)
+#define PECLR_ERR_DRIVER (-1002)
+#define PECLR_ERR_TENSORMAP (-1003)
+
+namespace peclr {
+
+constexpr int kMaxViews = 4;
+constexpr int kMaxTaps = 16;
+
+// bf16 tensor seen as (C, W, H, N) with C contiguous; strides in elements.
+struct View4 {
+  const void* ptr;
+  int64_t c, w, h, n;
+  int64_t sw, sh, sn;
+};
+
+// One entry per filter tap: which view to read, the pixel offset inside that view's lattice and the
+// column offset of the tap's weights inside the K dimension of the weight matrix.
+struct TapTable {
+  int8_t view[kMaxTaps];
+  int8_t dw[kMaxTaps];
+  int8_t dh[kMaxTaps];
+  int32_t koff[kMaxTaps];
+};
+
+void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn);
+
+// D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.
+int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
+                     float* stat_sumsq, int reduce_add, cudaStream_t stream);
+
+// dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin)
+int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
+                      int cin, int cout, float* dw, cudaStream_t stream);
+
+}  // namespace peclr

@@ -1,0 +1,294 @@
+"""Tensor-level wrappers over the C ABI (allocation + argument marshalling only; all arithmetic is in
+the CUDA kernels).  Layout conventions: activations NHWC bf16; conv weights bf16 [Cout][k*k][Cin]."""
+import numpy as np
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PeclrKernelError("peclr_b200 kernels need CUDA tensors (there is no CPU path)")
+        if t is not None and not t.is_contiguous():
+            raise _lib.PeclrKernelError("peclr_b200 kernels need contiguous tensors")
+
+
+# ------------------------------------------------------------------ convolutions
+def conv2d_fprop(x, w, k, stride, want_stats=False, out=None, stats=None):
+    """x [N,H,W,Cin] bf16, w [Cout,k*k,Cin] bf16 -> y [N,H/s,W/s,Cout] bf16 (+ stats [2,Cout] fp32)."""
+    _need_cuda(x, w)
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    y = out if out is not None else torch.empty((n, h // stride, wd // stride, cout), dtype=bf16, device=x.device)
+    if want_stats and stats is None:
+        stats = torch.zeros((2, cout), dtype=torch.float32, device=x.device)
+    _lib.call("peclr_conv2d_fprop", x, w, y, n, h, wd, cin, cout, k, stride,
+              stats[0] if stats is not None else None, stats[1] if stats is not None else None, _s())
+    return (y, stats) if want_stats else y
+
+
+def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False):
+    """dy [N,H/s,W/s,Cout], wt [Cin,k*k,Cout] -> dx [N,H,W,Cin]."""
+    _need_cuda(dy, wt)
+    n, h, wd, cin = in_shape
+    cout = dy.shape[-1]
+    dx = out if out is not None else torch.empty(in_shape, dtype=bf16, device=dy.device)
+    _lib.call("peclr_conv2d_dgrad", dy, wt, dx, n, h, wd, cin, cout, k, stride, int(accumulate), _s())
+    return dx
+
+
+def conv2d_wgrad(x, dy, k, stride, dw=None):
+    """dw [Cout,k*k,Cin] fp32 += dy^T im2col(x)."""
+    _need_cuda(x, dy)
+    n, h, wd, cin = x.shape
+    cout = dy.shape[-1]
+    if dw is None:
+        dw = torch.zeros((cout, k * k, cin), dtype=torch.float32, device=x.device)
+    _lib.call("peclr_conv2d_wgrad", x, dy, dw, n, h, wd, cin, cout, k, stride, _s())
+    return dw
+
+
+def stem_input(img1, img2, out=None):
+    """two fp32 NCHW batches -> zero-padded bf16 [2B, H+6, W+16, 4]."""
+    _need_cuda(img1, img2)
+    b, c, h, w = img1.shape
+    assert c == 3 and img2.shape == img1.shape and img1.dtype == torch.float32
+    if out is None:
+        out = torch.empty((2 * b, h + 6, w + 16, 4), dtype=bf16, device=img1.device)
+    _lib.call("peclr_stem_input", img1, img2, out, b, h, w, _s())
+    return out
+
+
+def stem_pack(w_master, out=None):
+    """(64,3,7,7) fp32 channels_last master -> [64,7,64] bf16 packed stem weights."""
+    assert w_master.shape == (64, 3, 7, 7)
+    flat = w_master.permute(0, 2, 3, 1)
+    assert flat.is_contiguous(), "stem weight must be stored channels_last"
+    if out is None:
+        out = torch.empty((64, 7, 64), dtype=bf16, device=w_master.device)
+    _lib.call("peclr_stem_pack", flat, out, _s())
+    return out
+
+
+def stem_fprop(xpad, wpack, h, w, want_stats=False, out=None, stats=None):
+    n = xpad.shape[0]
+    y = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=xpad.device)
+    if want_stats and stats is None:
+        stats = torch.zeros((2, 64), dtype=torch.float32, device=xpad.device)
+    _lib.call("peclr_stem_fprop", xpad, wpack, y, n, h, w,
+              stats[0] if stats is not None else None, stats[1] if stats is not None else None, _s())
+    return (y, stats) if want_stats else y
+
+
+def stem_wgrad(xpad, dy, h, w, dwpack=None):
+    n = xpad.shape[0]
+    if dwpack is None:
+        dwpack = torch.zeros((64, 7, 64), dtype=torch.float32, device=xpad.device)
+    _lib.call("peclr_stem_wgrad", xpad, dy, dwpack, n, h, w, _s())
+    return dwpack
+
+
+# ------------------------------------------------------------------ batch norm & friends
+def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=None, eps=1e-5, momentum=0.1, out=None):
+    """out = [relu](bn(y) + res).  res_bn = (stats, gamma, beta, running or None) if res is a raw conv output.
+    Returns out, (mean, invstd)[, (rmean, rinvstd)]."""
+    c = y.shape[-1]
+    m = y.numel() // c
+    dev = y.device
+    out = out if out is not None else torch.empty_like(y)
+    saved = torch.empty((2, c), dtype=torch.float32, device=dev)
+    rsaved = torch.empty((2, c), dtype=torch.float32, device=dev) if res_bn is not None else None
+    rstats, rgamma, rbeta, rrunning = res_bn if res_bn is not None else (None, None, None, None)
+    _lib.call(
+        "peclr_bn_apply", y, stats[0], stats[1], gamma, beta, res,
+        rstats[0] if rstats is not None else None, rstats[1] if rstats is not None else None, rgamma, rbeta,
+        out, saved[0], saved[1],
+        running[0] if running is not None else None, running[1] if running is not None else None,
+        rsaved[0] if rsaved is not None else None, rsaved[1] if rsaved is not None else None,
+        rrunning[0] if rrunning is not None else None, rrunning[1] if rrunning is not None else None,
+        m, c, eps, momentum, int(relu), _s())
+    return (out, saved, rsaved) if res_bn is not None else (out, saved)
+
+
+def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratch=None, dy=None, g_out=None):
+    """BatchNorm(+ReLU mask) backward.  dgamma/dbeta are accumulated in place.  Returns dy[, g]."""
+    c = y.shape[-1]
+    m = y.numel() // c
+    if scratch is None:
+        scratch = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+    dy = dy if dy is not None else torch.empty_like(y)
+    if want_g and g_out is None:
+        g_out = torch.empty_like(y)
+    _lib.call("peclr_bn_bwd_reduce", dout, mask, y, saved[0], saved[1], scratch, m, c, _s())
+    _lib.call("peclr_bn_bwd_apply", dout, mask, y, saved[0], saved[1], gamma, scratch, dy, g_out, dgamma, dbeta,
+              m, c, _s())
+    return (dy, g_out) if want_g else dy
+
+
+def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.1, out=None):
+    n, h, w, c = y.shape
+    assert c == 64
+    out = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=y.device)
+    saved = torch.empty((2, 64), dtype=torch.float32, device=y.device)
+    _lib.call("peclr_stem_bn_relu_pool", y, stats[0], stats[1], gamma, beta, out, saved[0], saved[1],
+              running[0] if running is not None else None, running[1] if running is not None else None,
+              n, h, w, eps, momentum, _s())
+    return out, saved
+
+
+def stem_pool_bn_backward(dpool, y, saved, gamma, beta, dgamma, dbeta, g_buf=None, scratch=None):
+    """Backward through maxpool + relu + stem BN.  Returns dy (grad of the raw stem conv output)."""
+    n, h, w, c = y.shape
+    if scratch is None:
+        scratch = torch.empty((128,), dtype=torch.float32, device=y.device)
+    g = g_buf if g_buf is not None else torch.empty_like(y)
+    _lib.call("peclr_stem_pool_bwd", dpool, y, saved[0], saved[1], gamma, beta, g, scratch, n, h, w, _s())
+    # pass 2: plain BN backward apply on the already masked gradient (in place: dy overwrites g)
+    _lib.call("peclr_bn_bwd_apply", g, None, y, saved[0], saved[1], gamma, scratch, g, None, dgamma, dbeta,
+              n * h * w, 64, _s())
+    return g
+
+
+def avgpool_fwd(x, out=None):
+    n, h, w, c = x.shape
+    out = out if out is not None else torch.empty((n, c), dtype=torch.float32, device=x.device)
+    _lib.call("peclr_avgpool_fwd", x, out, n, h * w, c, _s())
+    return out
+
+
+def avgpool_bwd(dout, shape, out=None):
+    n, h, w, c = shape
+    out = out if out is not None else torch.empty(shape, dtype=bf16, device=dout.device)
+    _lib.call("peclr_avgpool_bwd", dout, out, n, h * w, c, _s())
+    return out
+
+
+# ------------------------------------------------------------------ head (fp32)
+def linear_fwd(x, w, bias=None, out=None):
+    """x [M,K] @ w[N,K]^T (+ bias)."""
+    m, k = x.shape
+    n = w.shape[0]
+    out = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=x.device)
+    _lib.call("peclr_sgemm", x, w, out, bias, m, n, k, k, 1, 1, k, n, 0, _s())
+    return out
+
+
+def linear_dgrad(dy, w, out=None):
+    """dy [M,N] @ w [N,K] -> [M,K]."""
+    m, n = dy.shape
+    k = w.shape[1]
+    out = out if out is not None else torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    _lib.call("peclr_sgemm", dy, w, out, None, m, k, n, n, 1, k, 1, k, 0, _s())
+    return out
+
+
+def linear_wgrad(dy, x, dw):
+    """dw [N,K] += dy[M,N]^T @ x[M,K]."""
+    m, n = dy.shape
+    k = x.shape[1]
+    _lib.call("peclr_sgemm", dy, x, dw, None, n, k, m, 1, n, k, 1, k, 1, _s())
+    return dw
+
+
+def bn1d_relu_fwd(x, gamma, beta, running=None, eps=1e-5, momentum=0.1):
+    m, c = x.shape
+    out = torch.empty_like(x)
+    saved = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    _lib.call("peclr_bn1d_relu_fwd", x, gamma, beta, out, saved[0], saved[1],
+              running[0] if running is not None else None, running[1] if running is not None else None,
+              m, c, eps, momentum, _s())
+    return out, saved
+
+
+def bn1d_relu_bwd(dout, out, x, saved, gamma, dgamma, dbeta):
+    m, c = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("peclr_bn1d_relu_bwd", dout, out, x, saved[0], saved[1], gamma, dx, dgamma, dbeta, m, c, _s())
+    return dx
+
+
+def colsum_acc(x, out):
+    _lib.call("peclr_colsum_acc", x, out, x.shape[0], x.shape[1], _s())
+    return out
+
+
+# ------------------------------------------------------------------ fused loss
+STAT_NAMES = [f"proj{v}{c}_{s}" for v in (1, 2) for c in "xy" for s in ("mean", "median", "min", "max")]
+
+
+def ntxent_workspace(batch, world=1, device="cuda"):
+    nbytes = _lib.call("peclr_ntxent_workspace_bytes", batch, world)
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device)
+
+
+def ntxent_fused(p, angle, jx, jy, image_hw, crop, rotate, temperature=0.5, want_grad=True, workspace=None,
+                 world=1, rank=0, z_peers=None, flag_peers=None, epoch=0):
+    """Returns loss [1], stats [16], g_p (or None).  p [2B,128] fp32."""
+    _need_cuda(p, angle, jx, jy)
+    n, d = p.shape
+    b = n // 2
+    dev = p.device
+    if workspace is None:
+        workspace = ntxent_workspace(b, world, dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    stats = torch.empty((16,), dtype=torch.float32, device=dev)
+    g_p = torch.empty_like(p) if want_grad else None
+    _lib.call("peclr_ntxent_fused", p, angle if rotate else None, jx if crop else None, jy if crop else None,
+              b, d, int(image_hw[0]), int(image_hw[1]), int(crop), int(rotate), float(temperature), loss, stats, g_p,
+              workspace, workspace.numel() * 4, world, rank, z_peers, flag_peers, epoch, _s())
+    return loss, stats, g_p
+
+
+# ------------------------------------------------------------------ optimiser plumbing
+def build_opt_tables(seg_sizes, seg_wd, device):
+    """Flat-buffer segment / chunk tables for peclr_lars_adam_step."""
+    chunk = _lib.call("peclr_opt_chunk_elems")
+    begins = np.zeros(len(seg_sizes) + 1, dtype=np.int64)
+    begins[1:] = np.cumsum(seg_sizes)
+    cseg, cbeg = [], []
+    for t, (b, e) in enumerate(zip(begins[:-1], begins[1:])):
+        for s in range(int(b), int(e), chunk):
+            cseg.append(t)
+            cbeg.append(s)
+    return dict(
+        seg_begin=torch.tensor(begins, dtype=torch.int64, device=device),
+        seg_wd=torch.tensor(np.asarray(seg_wd, dtype=np.float32), device=device),
+        chunk_seg=torch.tensor(np.asarray(cseg, dtype=np.int32), device=device),
+        chunk_begin=torch.tensor(np.asarray(cbeg, dtype=np.int64), device=device),
+        norms=torch.zeros(2 * len(seg_sizes), dtype=torch.float32, device=device),
+        num_segs=len(seg_sizes), num_chunks=len(cseg),
+    )
+
+
+def lars_adam_step(p, g, m, v, tables, lr, step, p_bf16=None, lars=True, betas=(0.9, 0.999), adam_eps=1e-8,
+                   eta=0.02, clip=True, lars_eps=1e-8):
+    _lib.call("peclr_lars_adam_step", p, g, m, v, p_bf16, tables["seg_begin"], tables["seg_wd"], tables["num_segs"],
+              tables["chunk_seg"], tables["chunk_begin"], tables["num_chunks"], tables["norms"], float(lr), int(step),
+              betas[0], betas[1], adam_eps, int(lars), eta, int(clip), lars_eps, _s())
+
+
+TRANSPOSE_DTYPE = np.dtype([("src_off", "<i8"), ("dst_off", "<i8"), ("cout", "<i4"), ("taps", "<i4"),
+                            ("cin", "<i4"), ("tile_begin", "<i4")])
+
+
+def build_transpose_table(entries, device):
+    """entries: list of (src_off, dst_off, cout, taps, cin).  Returns (table tensor, num_entries, total_tiles)."""
+    tab = np.zeros(len(entries), dtype=TRANSPOSE_DTYPE)
+    tiles = 0
+    for i, (so, do, cout, taps, cin) in enumerate(entries):
+        tab[i] = (so, do, cout, taps, cin, tiles)
+        tiles += taps * ((cout + 31) // 32) * ((cin + 31) // 32)
+    t = torch.from_numpy(tab.view(np.uint8)).to(device)
+    return t, len(entries), tiles
+
+
+def weight_transpose(src_flat, dst_bf16, table):
+    t, n, tiles = table
+    _lib.call("peclr_weight_transpose", src_flat, dst_bf16, t, n, tiles, _s())

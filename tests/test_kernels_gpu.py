@@ -1,0 +1,351 @@
+"""Per-kernel parity on the B200: every CUDA kernel, called through the C ABI, against plain fp32 PyTorch on
+the same (bf16-rounded) operands, or against the oracle / golden vectors for the loss chain and optimiser.
+
+Tolerances: bf16-output kernels rel-L2 <= 1e-2 (bf16 output rounding is 2^-8); fp32
+kernels 1e-5 relative; the fused loss kernel |dloss| <= 1e-5 |loss|, gradient <= 1e-4 of the gradient scale
+against the reference's fp64 autograd.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from peclr_b200 import ops as _ops
+
+    return _ops
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def krsc(w):  # (Cout,Cin,kh,kw) -> [Cout, kh*kw, Cin]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1, w.shape[1]).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride
+    (4, 8, 8, 64, 64, 1, 1),
+    (2, 8, 8, 64, 256, 1, 1),
+    (3, 8, 8, 256, 64, 1, 1),
+    (4, 8, 8, 64, 64, 3, 1),
+    (2, 14, 14, 128, 128, 3, 1),
+    (32, 14, 14, 256, 256, 3, 1),
+    (4, 16, 16, 128, 128, 3, 2),
+    (4, 8, 8, 256, 512, 1, 2),
+    (16, 4, 4, 512, 2048, 1, 1),
+    (16, 56, 56, 64, 64, 3, 1),
+    (130, 2, 2, 512, 512, 3, 1),
+]
+
+
+def _conv_data(case, seed=0):
+    n, h, w, cin, cout, k, s = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16()
+    return x, wt
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_and_stats(ops, case):
+    n, h, w, cin, cout, k, s = case
+    x, wt = _conv_data(case)
+    ref = F.conv2d(x.float(), wt.float(), stride=s, padding=k // 2)
+    y, stats = ops.conv2d_fprop(nhwc(x), krsc(wt), k, s, want_stats=True)
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).float()
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
+    # statistics are those of the stored bf16 tensor
+    yf = y.float().reshape(-1, cout)
+    assert torch.allclose(stats[0], yf.sum(0), rtol=1e-3, atol=1e-2 * yf.abs().sum(0).max().item() / 100)
+    assert torch.allclose(stats[1], (yf * yf).sum(0), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(ops, case):
+    n, h, w, cin, cout, k, s = case
+    x, wt = _conv_data(case, 1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dy = torch.randn(n, cout, h // s, w // s, device="cuda", generator=g).bfloat16()
+    ref = torch.nn.grad.conv2d_input(x.shape, wt.float(), dy.float(), stride=s, padding=k // 2)
+    wt_t = krsc(wt).permute(2, 1, 0).contiguous()  # [Cin, taps, Cout]
+    dx = ops.conv2d_dgrad(nhwc(dy), wt_t, (n, h, w, cin), k, s)
+    torch.cuda.synchronize()
+    got = dx.permute(0, 3, 1, 2).float()
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
+    # accumulate on top of an existing gradient (TMA reduce-add)
+    base = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    acc = base.clone()
+    ops.conv2d_dgrad(nhwc(dy), wt_t, (n, h, w, cin), k, s, out=acc, accumulate=True)
+    torch.cuda.synchronize()
+    want = base.float() + nhwc(ref)
+    assert rel_l2(acc.float(), want) < 1.5e-2
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(ops, case):
+    n, h, w, cin, cout, k, s = case
+    x, wt = _conv_data(case, 3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    dy = torch.randn(n, cout, h // s, w // s, device="cuda", generator=g).bfloat16()
+    ref = torch.nn.grad.conv2d_weight(x.float(), wt.shape, dy.float(), stride=s, padding=k // 2)
+    dw = ops.conv2d_wgrad(nhwc(x), nhwc(dy), k, s)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, krsc(ref)) < 2e-3, rel_l2(dw, krsc(ref))  # fp32 accumulate + fp32 output
+    # accumulates
+    ops.conv2d_wgrad(nhwc(x), nhwc(dy), k, s, dw=dw)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, 2 * krsc(ref)) < 2e-3
+
+
+@pytest.mark.parametrize("n,hw", [(4, 32), (2, 64), (3, 224)])
+def test_stem(ops, n, hw):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b = n
+    img1 = torch.randn(b, 3, hw, hw, device="cuda", generator=g)
+    img2 = torch.randn(b, 3, hw, hw, device="cuda", generator=g)
+    w = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).contiguous(memory_format=torch.channels_last)
+    xpad = ops.stem_input(img1, img2)
+    x = torch.cat([img1, img2]).bfloat16()
+    assert torch.equal(xpad[:, 3:3 + hw, 3:3 + hw, :3], nhwc(x))
+    assert float(xpad[:, :3].abs().sum()) == 0 and float(xpad[..., 3].abs().sum()) == 0
+    wpack = ops.stem_pack(w)
+    ref = F.conv2d(x.float(), w.bfloat16().float(), stride=2, padding=3)
+    y, stats = ops.stem_fprop(xpad, wpack, hw, hw, want_stats=True)
+    torch.cuda.synchronize()
+    assert rel_l2(y.permute(0, 3, 1, 2).float(), ref) < 1e-2
+    yf = y.float().reshape(-1, 64)
+    assert torch.allclose(stats[0], yf.sum(0), rtol=1e-3, atol=1e-1)
+    dy = torch.randn(2 * b, 64, hw // 2, hw // 2, device="cuda", generator=g).bfloat16()
+    ref_dw = torch.nn.grad.conv2d_weight(x.float(), w.shape, dy.float(), stride=2, padding=3)
+    dwp = ops.stem_wgrad(xpad, nhwc(dy), hw, hw)
+    gw = torch.zeros(64, 3, 7, 7, device="cuda").contiguous(memory_format=torch.channels_last)
+    from peclr_b200 import _lib
+
+    _lib.call("peclr_stem_unpack_grad", dwp, gw.permute(0, 2, 3, 1), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_l2(gw, ref_dw) < 2e-3
+
+
+@pytest.mark.parametrize("c,m", [(64, 1000), (256, 777), (2048, 130)])
+def test_bn_apply_and_backward(ops, c, m):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    y = (torch.randn(m, c, device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    res = torch.randn(m, c, device="cuda", generator=g).bfloat16()
+    gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+    beta = torch.randn(c, device="cuda", generator=g)
+    yf = y.float()
+    stats = torch.stack([yf.sum(0), (yf * yf).sum(0)])
+    running = torch.stack([torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")])
+    out, saved = ops.bn_apply(y.view(m, 1, 1, c), stats, gamma, beta, relu=True, res=res.view(m, 1, 1, c), running=running)
+    # torch reference
+    yt = yf.clone().requires_grad_()
+    gt, bt = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    ref = torch.relu(F.batch_norm(yt, rm, rv, gt, bt, training=True, momentum=0.1, eps=1e-5) + res.float())
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().view(m, c), ref) < 1e-2
+    assert torch.allclose(running[0], rm, atol=1e-4) and torch.allclose(running[1], rv, rtol=1e-3, atol=1e-4)
+    dout = torch.randn(m, c, device="cuda", generator=g).bfloat16()
+    # use the kernel's own (bf16) output as the ReLU mask on both sides
+    mask = (out.float().view(m, c) > 0).float()
+    F.batch_norm(yt, None, None, gt, bt, training=True, eps=1e-5).backward(dout.float() * mask)
+    dgamma, dbeta = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dy, gout = ops.bn_backward(dout.view(m, 1, 1, c), out, y.view(m, 1, 1, c), saved, gamma, dgamma, dbeta, want_g=True)
+    torch.cuda.synchronize()
+    assert rel_l2(dy.float().view(m, c), yt.grad) < 1e-2
+    assert rel_l2(dgamma, gt.grad) < 2e-3 and rel_l2(dbeta, bt.grad) < 2e-3
+    assert torch.equal(gout.float().view(m, c), dout.float() * mask)
+
+
+def test_bn_apply_downsample_branch(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    m, c = 515, 256
+    y = torch.randn(m, c, device="cuda", generator=g).bfloat16()
+    yd = (torch.randn(m, c, device="cuda", generator=g) * 3).bfloat16()
+    gm, bt = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    gd, bd = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    st = lambda t: torch.stack([t.float().sum(0), (t.float() ** 2).sum(0)])
+    out, saved, rsaved = ops.bn_apply(y.view(m, 1, 1, c), st(y), gm, bt, relu=True, res=yd.view(m, 1, 1, c),
+                                      res_bn=(st(yd), gd, bd, None))
+    ref = torch.relu(F.batch_norm(y.float(), None, None, gm, bt, training=True)
+                     + F.batch_norm(yd.float(), None, None, gd, bd, training=True))
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().view(m, c), ref) < 1e-2
+    assert torch.allclose(rsaved[0], yd.float().mean(0), atol=1e-4)
+
+
+@pytest.mark.parametrize("n,hw", [(3, 16), (2, 112)])
+def test_stem_bn_relu_pool_fwd_bwd(ops, n, hw):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    y = torch.randn(n, hw, hw, 64, device="cuda", generator=g).bfloat16()
+    gamma = torch.rand(64, device="cuda", generator=g) + 0.5
+    gamma[::7] *= -1  # negative scales must work too
+    beta = torch.randn(64, device="cuda", generator=g) * 0.3
+    yf = y.float().reshape(-1, 64)
+    stats = torch.stack([yf.sum(0), (yf * yf).sum(0)])
+    out, saved = ops.stem_bn_relu_pool(y, stats, gamma, beta)
+    yt = y.float().permute(0, 3, 1, 2).clone().requires_grad_()
+    gt, bt = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    a = torch.relu(F.batch_norm(yt, None, None, gt, bt, training=True, eps=1e-5))
+    ref = F.max_pool2d(a, 3, 2, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(out.permute(0, 3, 1, 2).float(), ref) < 1e-2
+    dpool = torch.randn(n, hw // 2, hw // 2, 64, device="cuda", generator=g).bfloat16()
+    ref.backward(dpool.float().permute(0, 3, 1, 2))
+    dgamma, dbeta = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
+    dy = ops.stem_pool_bn_backward(dpool, y, saved, gamma, beta, dgamma, dbeta)
+    torch.cuda.synchronize()
+    assert rel_l2(dy.permute(0, 3, 1, 2).float(), yt.grad) < 2e-2
+    assert rel_l2(dgamma, gt.grad) < 1e-2 and rel_l2(dbeta, bt.grad) < 1e-2
+
+
+def test_avgpool(ops):
+    x = torch.randn(6, 7, 7, 2048, device="cuda").bfloat16()
+    out = ops.avgpool_fwd(x)
+    assert torch.allclose(out, x.float().mean((1, 2)), atol=1e-5)
+    d = torch.randn(6, 2048, device="cuda")
+    dx = ops.avgpool_bwd(d, x.shape)
+    assert rel_l2(dx.float(), (d / 49)[:, None, None, :].expand(6, 7, 7, 2048)) < 5e-3
+
+
+@pytest.mark.parametrize("m", [16, 256])
+def test_head_kernels(ops, m):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(m, 2048, device="cuda", generator=g)
+    w1 = torch.randn(512, 2048, device="cuda", generator=g) / 45
+    b1 = torch.randn(512, device="cuda", generator=g)
+    w2 = torch.randn(128, 512, device="cuda", generator=g) / 22
+    gamma, beta = torch.rand(512, device="cuda") + 0.5, torch.randn(512, device="cuda")
+    xs = [t.clone().requires_grad_() for t in (x, w1, b1, gamma, beta, w2)]
+    h_ref = F.linear(xs[0], xs[1], xs[2])
+    rm, rv = torch.zeros(512, device="cuda"), torch.ones(512, device="cuda")
+    a_ref = torch.relu(F.batch_norm(h_ref, rm, rv, xs[3], xs[4], training=True))
+    p_ref = F.linear(a_ref, xs[5])
+    h = ops.linear_fwd(x, w1, b1)
+    running = torch.stack([torch.zeros(512, device="cuda"), torch.ones(512, device="cuda")])
+    a, saved = ops.bn1d_relu_fwd(h, gamma, beta, running)
+    p = ops.linear_fwd(a, w2)
+    torch.cuda.synchronize()
+    assert rel_l2(h, h_ref) < 1e-5 and rel_l2(a, a_ref) < 1e-5 and rel_l2(p, p_ref) < 1e-5
+    assert torch.allclose(running[0], rm, atol=1e-5) and torch.allclose(running[1], rv, rtol=1e-4)
+    gp = torch.randn(m, 128, device="cuda", generator=g)
+    p_ref.backward(gp)
+    dw2 = ops.linear_wgrad(gp, a, torch.zeros_like(w2))
+    da = ops.linear_dgrad(gp, w2)
+    dgamma, dbeta = torch.zeros(512, device="cuda"), torch.zeros(512, device="cuda")
+    dh = ops.bn1d_relu_bwd(da, a, h, saved, gamma, dgamma, dbeta)
+    dw1 = ops.linear_wgrad(dh, x, torch.zeros_like(w1))
+    db1 = ops.colsum_acc(dh, torch.zeros(512, device="cuda"))
+    dx = ops.linear_dgrad(dh, w1)
+    torch.cuda.synchronize()
+    for got, want in ((dw2, xs[5].grad), (dgamma, xs[3].grad), (dbeta, xs[4].grad), (dw1, xs[1].grad),
+                      (db1, xs[2].grad), (dx, xs[0].grad)):
+        assert rel_l2(got, want) < 2e-4, rel_l2(got, want)
+
+
+def test_ntxent_fused_against_reference_goldens(ops, golden_dir):
+    chain = np.load(os.path.join(golden_dir, "loss_chain.npz"))
+    for name in chain["cases"]:
+        g = lambda k: chain[f"{name}_{k}"]
+        crop, rotate = (bool(v) for v in g("flags"))
+        p = torch.tensor(g("p"), device="cuda")
+        loss, stats, g_p = ops.ntxent_fused(
+            p, torch.tensor(g("angle"), device="cuda", dtype=torch.float64),
+            torch.tensor(g("jx"), device="cuda", dtype=torch.int64), torch.tensor(g("jy"), device="cuda", dtype=torch.int64),
+            tuple(int(v) for v in g("hw")), crop, rotate)
+        torch.cuda.synchronize()
+        l64 = float(g("loss64"))
+        assert abs(loss.item() - l64) <= 1e-5 * max(1.0, abs(l64)), (name, loss.item(), l64)
+        g64 = g("g64")
+        scale = np.abs(g64).max()
+        err = np.abs(g_p.cpu().numpy() - g64).max()
+        assert err <= 1e-4 * scale + 1e-9, (name, err, scale)
+        want = dict(zip(g("stat_names"), g("stats")))
+        for i, sn in enumerate(ops.STAT_NAMES):
+            assert abs(stats[i].item() - want[sn]) <= 2e-6 * max(1.0, abs(want[sn])) + 1e-6, (name, sn)
+        # forward-only variant gives the same loss
+        loss2, _, none = ops.ntxent_fused(
+            p, torch.tensor(g("angle"), device="cuda", dtype=torch.float64),
+            torch.tensor(g("jx"), device="cuda", dtype=torch.int64), torch.tensor(g("jy"), device="cuda", dtype=torch.int64),
+            tuple(int(v) for v in g("hw")), crop, rotate, want_grad=False)
+        assert none is None and abs(loss2.item() - loss.item()) < 1e-6
+
+
+def test_ntxent_fused_large_batch_vs_oracle(ops):
+    """2N = 2048 rows (the 8-GPU global batch of BASELINE config 3) against the fp64 closed-form oracle."""
+    from oracle import peclr_oracle as po
+
+    rng = np.random.RandomState(0)
+    b = 1024
+    p = rng.randn(2 * b, 128).astype(np.float32)
+    p[b:] = p[:b] + 0.5 * rng.randn(b, 128).astype(np.float32)
+    angle = np.floor(rng.uniform(-45, 45, 2 * b))
+    jx, jy = -rng.randint(0, 15, 2 * b), -rng.randint(0, 15, 2 * b)
+    ref = po.loss_chain_numpy(p, angle, jx, jy, (224, 224), True, True, dtype=np.float64)
+    loss, stats, g_p = ops.ntxent_fused(torch.tensor(p, device="cuda"), torch.tensor(angle, device="cuda"),
+                                        torch.tensor(jx, device="cuda"), torch.tensor(jy, device="cuda"),
+                                        (224, 224), True, True)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert np.abs(g_p.cpu().numpy() - ref["g_p"]).max() <= 1e-4 * np.abs(ref["g_p"]).max()
+
+
+def test_lars_adam_step_vs_oracle(ops):
+    from oracle import peclr_oracle as po
+
+    rng = np.random.RandomState(1)
+    sizes = [64 * 147, 64, 64, 70000, 1, 512 * 2048 + 3]
+    wds = [1e-6, 0.0, 0.0, 1e-6, 0.0, 1e-6]
+    tot = sum(sizes)
+    tables = ops.build_opt_tables(sizes, wds, "cuda")
+    p0 = rng.randn(tot).astype(np.float32)
+    p0[sizes[0]:sizes[0] + 64] = 0  # a zero tensor: LARS must leave its gradient untouched
+    for lars, lr in ((True, 1.131e-3), (True, 0.0), (False, 2e-3)):
+        p = torch.tensor(p0, device="cuda")
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        pb = torch.empty(tot, dtype=torch.bfloat16, device="cuda")
+        ref = [(p0[b:e].copy(), np.zeros(e - b, np.float32), np.zeros(e - b, np.float32))
+               for b, e in zip(np.cumsum([0] + sizes[:-1]), np.cumsum(sizes))]
+        for step in (1, 2, 3):
+            gnp = (rng.randn(tot) * 10.0 ** (-step)).astype(np.float32)
+            ops.lars_adam_step(p, torch.tensor(gnp, device="cuda"), m, v, tables, lr, step, p_bf16=pb, lars=lars)
+            off = 0
+            for i, sz in enumerate(sizes):
+                ref[i] = po.lars_adam_step_numpy(ref[i][0], gnp[off:off + sz], ref[i][1], ref[i][2], step, lr, wds[i], lars=lars)
+                off += sz
+        torch.cuda.synchronize()
+        want = np.concatenate([r[0] for r in ref])
+        got = p.cpu().numpy()
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max() + 1e-7, (lars, lr, np.abs(got - want).max())
+        assert torch.equal(pb, p.bfloat16())
+
+
+def test_weight_transpose_and_cast(ops):
+    from peclr_b200 import _lib
+
+    w1 = torch.randn(128, 9, 64, device="cuda")
+    w2 = torch.randn(256, 1, 1024, device="cuda")
+    flat = torch.cat([w1.flatten(), torch.randn(77, device="cuda"), w2.flatten()])
+    dst = torch.zeros(w1.numel() + w2.numel(), dtype=torch.bfloat16, device="cuda")
+    table = ops.build_transpose_table([(0, 0, 128, 9, 64), (w1.numel() + 77, w1.numel(), 256, 1, 1024)], "cuda")
+    ops.weight_transpose(flat, dst, table)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[: w1.numel()].view(64, 9, 128), w1.permute(2, 1, 0).bfloat16())
+    assert torch.equal(dst[w1.numel():].view(1024, 1, 256), w2.permute(2, 1, 0).bfloat16())
+    out = torch.empty(flat.numel(), dtype=torch.bfloat16, device="cuda")
+    _lib.call("peclr_cast_bf16", flat, out, flat.numel(), _lib.stream_ptr())
+    assert torch.equal(out, flat.bfloat16())
