@@ -107,6 +107,12 @@ int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx,
                        float* g_p, void* workspace, long long workspace_bytes, int world, int rank,
                        float* const* z_peers, unsigned* const* flag_peers, unsigned epoch, void* stream);
 
+/* NT-Xent alone on already-normalised embeddings z [2B][128] (view-1 rows then view-2 rows): the same kernel
+ * without the normalisation / correction phases.  Replaces vanila_contrastive_loss (src/models/utils.py:154-186)
+ * as used by SimCLR.contrastive_step (simclr_model.py:37-49).  g_z = dloss/dz (NULL: forward only). */
+int peclr_ntxent_plain(const float* z, int B, int dim, float temperature, float* loss, float* g_z, void* workspace,
+                       long long workspace_bytes, void* stream);
+
 /* ---- fused LARS-Adam over the flat parameter buffer (csrc/lars_adam.cu); replaces
  * LARSWrapper(torch.optim.Adam).step() as configured by BaseModel.configure_optimizers
  * (src/models/base_model.py:57-104).  seg_begin[num_segs+1] are tensor boundaries, seg_wd the weight

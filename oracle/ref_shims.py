@@ -150,7 +150,11 @@ def load_reference():
     saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
     for k in saved:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
+    # (the reference's ``src`` has no __init__.py -> it is a namespace package and would lose to this repo's
+    # regular ``src`` package wherever it sits on sys.path, so the repo root is taken off the path meanwhile)
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in saved_path if os.path.abspath(p or os.getcwd()) != repo_root]
     try:
         import importlib
 
@@ -178,7 +182,7 @@ def load_reference():
             EasyDict=_AttrDict,
         )
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
         ref_mods = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
         for k in ref_mods:
             del sys.modules[k]

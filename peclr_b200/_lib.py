@@ -36,6 +36,7 @@ SIGNATURES = {
     "peclr_colsum_acc": [P, P, I, I, P],
     "peclr_ntxent_workspace_bytes": [I, I],
     "peclr_ntxent_fused": [P, P, P, P, I, I, I, I, I, I, F, P, P, P, P, L, I, I, P, P, c_uint, P],
+    "peclr_ntxent_plain": [P, I, I, F, P, P, P, L, P],
     "peclr_opt_chunk_elems": [],
     "peclr_lars_adam_step": [P, P, P, P, P, P, P, I, P, P, I, P, F, I, F, F, F, I, F, I, F, P],
     "peclr_cast_bf16": [P, P, L, P],
@@ -80,8 +81,21 @@ def _check(name, rc):
         raise PeclrKernelError(f"{name} failed: {rc} ({what})")
 
 
+LAUNCHES = 0  # kernels of this library launched so far (bench.py reports the count of the timed region)
+_PROFILE = None
+
+
+def _kernels_in_call(name, args):
+    if name == "peclr_conv2d_dgrad":
+        return 4 if (args[8] == 3 and args[9] == 2) else 1
+    if name == "peclr_lars_adam_step":
+        return 2 if args[17] else 1
+    return 1
+
+
 def call(name, *args):
     """Calls an entry point, converting torch tensors to device pointers; raises on a non-zero return."""
+    global LAUNCHES
     lib = load()
     conv = []
     for a in args:
@@ -89,11 +103,36 @@ def call(name, *args):
             conv.append(a.data_ptr())
         else:
             conv.append(a)
-    rc = getattr(lib, name)(*conv)
     if name in _NO_CHECK:
-        return rc
+        return getattr(lib, name)(*conv)
+    prof = _PROFILE is not None and name in _PROFILE["names"]
+    if prof:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*conv)
+    if prof:
+        e1.record()
+        _PROFILE["records"].append((name, args, e0, e1))
     _check(name, rc)
+    LAUNCHES += _kernels_in_call(name, args)
     return rc
+
+
+def profile_calls(fn, names):
+    """Runs fn() with every call to the named entry points bracketed by CUDA events on the launching stream.
+    Returns [(name, args, milliseconds)]."""
+    global _PROFILE
+    import torch
+
+    _PROFILE = {"names": set(names), "records": []}
+    try:
+        fn()
+        torch.cuda.synchronize()
+        return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in _PROFILE["records"]]
+    finally:
+        _PROFILE = None
 
 
 def stream_ptr():

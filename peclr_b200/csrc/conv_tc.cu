@@ -41,6 +41,8 @@ struct GemmParams {
   int num_taps, c_chunks;
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int Wb, Hb, Nb;
+  int log_wb, log_wbhb;
+  int d_w, d_h, d_n;
   int cout;
   float* stat_sum;
   float* stat_sumsq;
@@ -215,14 +217,30 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         const int c16 = (col & 63) >> 3;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         if (rg < kRowGroups) {
+          // rows of a box that hangs over the image edge are clipped by the TMA store: keep them out of
+          // the statistics too (their taps can still reach valid pixels, so they are not zero)
+          const bool edge = w0 + p.Wb > p.d_w || h0 + p.Hb > p.d_h || n0 + p.Nb > p.d_n;
+          if (!edge) {
 #pragma unroll 4
-          for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
-            const float a = bf16_lo(v), b = bf16_hi(v);
-            s0 += a;
-            s1 += b;
-            q0 = fmaf(a, a, q0);
-            q1 = fmaf(b, b, q1);
+            for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
+              const float a = bf16_lo(v), b = bf16_hi(v);
+              s0 += a;
+              s1 += b;
+              q0 = fmaf(a, a, q0);
+              q1 = fmaf(b, b, q1);
+            }
+          } else {
+            for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
+              const int wl = r0 & (p.Wb - 1), hl = (r0 >> p.log_wb) & (p.Hb - 1), nl = r0 >> p.log_wbhb;
+              if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) continue;
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
+              const float a = bf16_lo(v), b = bf16_hi(v);
+              s0 += a;
+              s1 += b;
+              q0 = fmaf(a, a, q0);
+              q1 = fmaf(b, b, q1);
+            }
           }
           float* ss = sStat + nt * BN + col;
           atomicAdd(ss, s0);
@@ -467,8 +485,9 @@ void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn) {
       const int n = target / (w * h);
       if (w > 256 || h > 256 || n > 256) continue;
       const long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
-      // fewer tiles first; then wider boxes (longer contiguous runs)
-      if (best < 0 || tiles < best || (tiles == best && w > *bw)) {
+      // fewer tiles first; then larger spatial patches (filter-halo reuse in L2), then wider boxes
+      if (best < 0 || tiles < best ||
+          (tiles == best && (w * h > *bw * *bh || (w * h == *bw * *bh && w > *bw)))) {
         best = tiles;
         *bw = w;
         *bh = h;
@@ -522,6 +541,9 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.num_taps = num_taps;
   p.c_chunks = c_chunks;
   p.Wb = bw, p.Hb = bh, p.Nb = bn;
+  p.log_wb = __builtin_ctz(bw);
+  p.log_wbhb = __builtin_ctz(bw * bh);
+  p.d_w = (int)d_view.w, p.d_h = (int)d_view.h, p.d_n = (int)d_view.n;
   p.tiles_w = (int)((d_view.w + bw - 1) / bw);
   p.tiles_h = (int)((d_view.h + bh - 1) / bh);
   p.tiles_n = (int)((d_view.n + bn - 1) / bn);

@@ -52,6 +52,7 @@ struct NtxentArgs {
   float inv_t;
   unsigned epoch;
   int col_chunk;           // columns per P3 unit (multiple of CB)
+  int plain;               // 1: p already holds z (plain NT-Xent, no normalisation / correction / stats)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
@@ -98,12 +99,17 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
 
   // ---------------------------------------------------------------- P1
   if (blockIdx.x == 0 && threadIdx.x < 17) {
-    if (threadIdx.x < 16) a.stats[threadIdx.x] = 0.f;
-    else *a.loss = 0.f;
+    if (threadIdx.x == 16) *a.loss = 0.f;
+    else if (a.stats) a.stats[threadIdx.x] = 0.f;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_glob; i += gridDim.x * blockDim.x) a.neg[i] = 0.f;
   for (int i = gwarp; i < n_loc; i += nwarps) {
     const float4 v = reinterpret_cast<const float4*>(a.p + (size_t)i * D)[lane];  // points 2l, 2l+1
+    if (a.plain) {
+      reinterpret_cast<float4*>(a.z + (size_t)global_row(i, a.B, a.world, a.rank) * D)[lane] = v;
+      if (a.g_p) reinterpret_cast<float4*>(a.gz + (size_t)i * D)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     float x0 = v.x, y0 = v.y, x1 = v.z, y1 = v.w;
     // projection statistics of the raw head output (hybrid2_model.py:92-106), detached
     {
@@ -331,6 +337,10 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   if (!a.g_p) return;
   for (int i = gwarp; i < n_loc; i += nwarps) {
     const int gi = global_row(i, a.B, a.world, a.rank);
+    if (a.plain) {
+      reinterpret_cast<float4*>(a.g_p + (size_t)i * D)[lane] = reinterpret_cast<const float4*>(a.gz + (size_t)i * D)[lane];
+      continue;
+    }
     const float4 rb = reinterpret_cast<const float4*>(a.rowbuf)[i];
     const float inv_p = rb.x, inv_r = rb.y, al = rb.z, be = rb.w;
     const float4 zv = reinterpret_cast<const float4*>(a.z + (size_t)gi * D)[lane];
@@ -367,11 +377,11 @@ extern "C" long long peclr_ntxent_workspace_bytes(int B, int world) {
   return 4 * (n_glob * D + n_loc * 4 + 2 * n_glob + n_loc * D) + 256;
 }
 
-extern "C" int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
-                                  int dim, int img_h, int img_w, int crop, int rotate, float temperature, float* loss,
-                                  float* stats, float* g_p, void* workspace, long long workspace_bytes, int world,
-                                  int rank, float* const* z_peers, unsigned* const* flag_peers, unsigned epoch,
-                                  void* stream) {
+static int ntxent_launch(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
+                         int dim, int img_h, int img_w, int crop, int rotate, float temperature, float* loss,
+                         float* stats, float* g_p, void* workspace, long long workspace_bytes, int world, int rank,
+                         float* const* z_peers, unsigned* const* flag_peers, unsigned epoch, int plain,
+                         void* stream) {
   if (dim != D || B < 1 || world < 1 || rank < 0 || rank >= world) return -1001;
   if (workspace_bytes < peclr_ntxent_workspace_bytes(B, world)) return -1001;
   if ((crop && (!jx || !jy)) || (rotate && !angle)) return -1001;
@@ -392,6 +402,7 @@ extern "C" int peclr_ntxent_fused(const float* p, const double* angle, const lon
   a.img_h = img_h, a.img_w = img_w, a.crop = crop, a.rotate = rotate;
   a.inv_t = 1.f / temperature;
   a.epoch = epoch;
+  a.plain = plain;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -414,4 +425,20 @@ extern "C" int peclr_ntxent_fused(const float* p, const double* angle, const lon
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)ntxent_fused_kernel, dim3(grid), dim3(256), args, smem, st);
   return e == cudaSuccess ? 0 : -(int)e;
+}
+
+extern "C" int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
+                                  int dim, int img_h, int img_w, int crop, int rotate, float temperature, float* loss,
+                                  float* stats, float* g_p, void* workspace, long long workspace_bytes, int world,
+                                  int rank, float* const* z_peers, unsigned* const* flag_peers, unsigned epoch,
+                                  void* stream) {
+  if (!stats) return -1001;
+  return ntxent_launch(p, angle, jx, jy, B, dim, img_h, img_w, crop, rotate, temperature, loss, stats, g_p,
+                       workspace, workspace_bytes, world, rank, z_peers, flag_peers, epoch, 0, stream);
+}
+
+extern "C" int peclr_ntxent_plain(const float* z, int B, int dim, float temperature, float* loss, float* g_z,
+                                  void* workspace, long long workspace_bytes, void* stream) {
+  return ntxent_launch(z, nullptr, nullptr, nullptr, B, dim, 1, 1, 0, 0, temperature, loss, nullptr, g_z, workspace,
+                       workspace_bytes, 1, 0, nullptr, nullptr, 0, 1, stream);
 }

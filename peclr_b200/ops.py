@@ -96,15 +96,18 @@ def stem_wgrad(xpad, dy, h, w, dwpack=None):
 
 
 # ------------------------------------------------------------------ batch norm & friends
-def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=None, eps=1e-5, momentum=0.1, out=None):
+def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=None, eps=1e-5, momentum=0.1, out=None,
+             saved=None, rsaved=None):
     """out = [relu](bn(y) + res).  res_bn = (stats, gamma, beta, running or None) if res is a raw conv output.
     Returns out, (mean, invstd)[, (rmean, rinvstd)]."""
     c = y.shape[-1]
     m = y.numel() // c
     dev = y.device
     out = out if out is not None else torch.empty_like(y)
-    saved = torch.empty((2, c), dtype=torch.float32, device=dev)
-    rsaved = torch.empty((2, c), dtype=torch.float32, device=dev) if res_bn is not None else None
+    if saved is None:
+        saved = torch.empty((2, c), dtype=torch.float32, device=dev)
+    if rsaved is None and res_bn is not None:
+        rsaved = torch.empty((2, c), dtype=torch.float32, device=dev)
     rstats, rgamma, rbeta, rrunning = res_bn if res_bn is not None else (None, None, None, None)
     _lib.call(
         "peclr_bn_apply", y, stats[0], stats[1], gamma, beta, res,
@@ -132,11 +135,12 @@ def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratc
     return (dy, g_out) if want_g else dy
 
 
-def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.1, out=None):
+def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.1, out=None, saved=None):
     n, h, w, c = y.shape
     assert c == 64
     out = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=y.device)
-    saved = torch.empty((2, 64), dtype=torch.float32, device=y.device)
+    if saved is None:
+        saved = torch.empty((2, 64), dtype=torch.float32, device=y.device)
     _lib.call("peclr_stem_bn_relu_pool", y, stats[0], stats[1], gamma, beta, out, saved[0], saved[1],
               running[0] if running is not None else None, running[1] if running is not None else None,
               n, h, w, eps, momentum, _s())
@@ -244,6 +248,18 @@ def ntxent_fused(p, angle, jx, jy, image_hw, crop, rotate, temperature=0.5, want
               b, d, int(image_hw[0]), int(image_hw[1]), int(crop), int(rotate), float(temperature), loss, stats, g_p,
               workspace, workspace.numel() * 4, world, rank, z_peers, flag_peers, epoch, _s())
     return loss, stats, g_p
+
+
+def ntxent_plain(z, temperature=0.5, want_grad=True, workspace=None):
+    """NT-Xent on already-normalised z [2B,128].  Returns loss [1], None, g_z."""
+    _need_cuda(z)
+    n, d = z.shape
+    if workspace is None:
+        workspace = ntxent_workspace(n // 2, 1, z.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+    g = torch.empty_like(z) if want_grad else None
+    _lib.call("peclr_ntxent_plain", z, n // 2, d, float(temperature), loss, g, workspace, workspace.numel() * 4, _s())
+    return loss, None, g
 
 
 # ------------------------------------------------------------------ optimiser plumbing

@@ -253,8 +253,10 @@ def test_head_kernels(ops, m):
     dx = ops.linear_dgrad(dh, w1)
     torch.cuda.synchronize()
     for got, want in ((dw2, xs[5].grad), (dgamma, xs[3].grad), (dbeta, xs[4].grad), (dw1, xs[1].grad),
-                      (db1, xs[2].grad), (dx, xs[0].grad)):
+                      (dx, xs[0].grad)):
         assert rel_l2(got, want) < 2e-4, rel_l2(got, want)
+    # a bias in front of a training-mode BatchNorm has an analytically zero gradient: both are rounding noise
+    assert db1.abs().max() < 1e-4 * dh.abs().sum(0).max() and xs[2].grad.abs().max() < 1e-4
 
 
 def test_ntxent_fused_against_reference_goldens(ops, golden_dir):
