@@ -83,8 +83,8 @@ class BaseModel(LightningModule):
         cfg = self.config
         # encoder.final_layer never receives a gradient in pre-training (torch.optim.Adam skips it in the
         # reference, base_model.py:62); it is not part of the fused optimiser's flat buffer.
-        named = [(n, p) for n, p in self.named_parameters() if not n.startswith("encoder.final_layer")]
-        groups = self.exclude_from_wt_decay(named, weight_decay=cfg.opt_weight_decay)
+        # it stays in the param groups (as in the reference) but not in the fused optimiser's flat buffer.
+        groups = self.exclude_from_wt_decay(self.named_parameters(), weight_decay=cfg.opt_weight_decay)
         lr = cfg.lr * math.sqrt(cfg.batch_size * cfg.num_of_mini_batch)
         warmup = cfg.warmup_epochs * self.train_iters_per_epoch // cfg.num_of_mini_batch
         if "lr_max_epochs" in cfg.keys() and cfg["lr_max_epochs"] is not None:

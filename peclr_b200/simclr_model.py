@@ -27,7 +27,7 @@ class _StepFunction(torch.autograd.Function):
         eng.backward_trunk(d_enc, ctx.trunk_ctx, after_stage=ctx.model._after_stage_hook)
         eng.attach_grads()
         ctx.g_p = ctx.head_ctx = ctx.trunk_ctx = None
-        return torch.zeros_like(anchor), None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class SimCLR(BaseModel):

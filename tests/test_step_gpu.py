@@ -38,6 +38,7 @@ def make_pair(warm_steps):
             opt.zero_grad()
             oracle.training_step(batch, i)["loss"].backward()
             opt.step()
+    oracle.train_metrics, oracle.plot_params = {}, {}  # hold graph tensors: not deep-copyable
     torch.manual_seed(0)
     ours = Hybrid2Model(EasyDict(dict(cfg)))
     ours.load_state_dict(oracle.state_dict())
