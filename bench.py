@@ -116,10 +116,28 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
 
-    def step(batch):
+    def eager_step(batch):
         opt.zero_grad()
         out = model.training_step(batch, 0)
         out["loss"].backward()
+        model.sync_gradients()
+        opt.step()
+        sched.step()
+        return out["loss"]
+
+    graphed = None
+    if not args.no_graph:
+        from peclr_b200.graphed import GraphedStep
+
+        graphed = GraphedStep(model, resident[0], grad_scale=1.0)
+
+    def step(batch):
+        """One optimiser step.  With the CUDA graph, training_step + backward are replayed from the capture
+        (same kernels, one submission); gradient exchange and the fused optimiser run after it."""
+        if graphed is None:
+            return eager_step(batch)
+        opt.zero_grad()
+        out = graphed(batch)
         model.sync_gradients()
         opt.step()
         sched.step()
@@ -201,7 +219,7 @@ def run_ours(args):
     cpu = None
     if rank == 0:
         pk = peaks()
-        prof = _lib.profile_calls(lambda: step(resident[0]),
+        prof = _lib.profile_calls(lambda: eager_step(resident[0]),
                                   {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_wgrad",
                                    "peclr_stem_fprop", "peclr_stem_wgrad"})
         flops = {"gemm": 0.0, "wgrad": 0.0}
@@ -343,6 +361,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="submit kernels eagerly (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

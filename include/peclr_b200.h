@@ -59,20 +59,25 @@ int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const fl
                    void* out, float* mean_out, float* invstd_out, float* running_mean, float* running_var,
                    float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
                    float eps, float momentum, int relu, void* stream);
-/* scratch[0:C] = sum g, scratch[C:2C] = sum g*xhat with g = dout * [mask > 0] (mask NULL: g = dout) */
+/* scratch[0:C] = sum g, scratch[C:2C] = sum g*xhat with g = dout * relu'; the ReLU mask is (mask_mode)
+ * 0: none (dout already masked), 1: the stored activation `mask` > 0, 2: recomputed from y, gamma, beta. */
 int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
-                        float* scratch, long long M, int C, void* stream);
+                        const float* gamma, const float* beta, int mask_mode, float* scratch, long long M, int C,
+                        void* stream);
 /* dy = gamma*invstd*(g - mean g - xhat*mean(g xhat)); optional g_out = g; dgamma/dbeta += scratch */
 int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
-                       const float* gamma, const float* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
-                       long long M, int C, void* stream);
-/* out[N,H/2,W/2,64] = maxpool3x3s2p1(relu(bn(y[N,H,W,64])))   (features.1-3) */
+                       const float* gamma, const float* beta, int mask_mode, const float* scratch, void* dy,
+                       void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream);
+/* out[N,H/2,W/2,64] = maxpool3x3s2p1(relu(bn(y[N,H,W,64])))   (features.1-3); idx_out (uint8, same shape as
+ * out, may be NULL) records the winning window position 0..8 for the backward pass */
 int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
-                            const float* beta, void* out, float* mean_out, float* invstd_out, float* running_mean,
-                            float* running_var, int N, int H, int W, float eps, float momentum, void* stream);
+                            const float* beta, void* out, void* idx_out, float* mean_out, float* invstd_out,
+                            float* running_mean, float* running_var, int N, int H, int W, float eps, float momentum,
+                            void* stream);
 /* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums into scratch[128] */
-int peclr_stem_pool_bwd(const void* dpool, const void* y, const float* mean, const float* invstd, const float* gamma,
-                        const float* beta, void* g_out, float* scratch, int N, int H, int W, void* stream);
+int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, void* g_out, float* scratch, int N, int H, int W,
+                        void* stream);
 int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
 int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream);
 /* cat(transformed_image1, transformed_image2) (hybrid2_model.py:30-32), fp32 NCHW -> padded bf16 NHWC4 */

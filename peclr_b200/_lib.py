@@ -23,10 +23,10 @@ SIGNATURES = {
     "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
     "peclr_stem_wgrad": [P, P, P, I, I, I, P],
     "peclr_bn_apply": [P] * 19 + [L, I, F, F, I, P],
-    "peclr_bn_bwd_reduce": [P, P, P, P, P, P, L, I, P],
-    "peclr_bn_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, L, I, P],
-    "peclr_stem_bn_relu_pool": [P] * 10 + [I, I, I, F, F, P],
-    "peclr_stem_pool_bwd": [P] * 8 + [I, I, I, P],
+    "peclr_bn_bwd_reduce": [P, P, P, P, P, P, P, I, P, L, I, P],
+    "peclr_bn_bwd_apply": [P, P, P, P, P, P, P, I, P, P, P, P, P, L, I, P],
+    "peclr_stem_bn_relu_pool": [P] * 11 + [I, I, I, F, F, P],
+    "peclr_stem_pool_bwd": [P] * 9 + [I, I, I, P],
     "peclr_avgpool_fwd": [P, P, I, I, I, P],
     "peclr_avgpool_bwd": [P, P, I, I, I, P],
     "peclr_stem_input": [P, P, P, I, I, I, P],

@@ -3,9 +3,9 @@
 // global average pool, and the NCHW fp32 -> padded NHWC4 bf16 input transform.
 //
 // All activation tensors are [M = N*H*W][C] bf16 with C contiguous; every thread owns 8 consecutive
-// channels (one 16-byte vector) and walks rows, so loads/stores are fully coalesced 128-bit accesses
-// and the per-channel BatchNorm coefficients live in registers.  Grids are sized in multiples of the
-// SM count.
+// channels (one 16-byte vector), keeps the per-channel BatchNorm coefficients in registers and walks
+// rows with kRows independent 128-bit loads in flight, so accesses are fully coalesced and the memory
+// system sees enough parallelism.  Grids are sized in multiples of the SM count.
 //
 // Replaces ATen/cuDNN BatchNorm2d(train) + ReLU + residual add + MaxPool2d + AdaptiveAvgPool2d of the
 // reference trunk (src/models/resnet_model.py:16-26; torchvision ResNet.forward).
@@ -13,6 +13,8 @@
 #include "ptx.cuh"
 
 namespace peclr {
+
+constexpr int kRows = 4;  // rows (16-byte loads) in flight per thread
 
 struct alignas(16) bf16x8 {
   uint32_t v[4];
@@ -31,7 +33,15 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) p.v[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
   return p;
 }
-__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+// streaming 128-bit load (read once: do not pollute L1) / plain 128-bit store
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
+  bf16x8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ bf16x8 ld8_cached(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
 // mean / inverse std of 8 channels from the sums the convolution epilogue accumulated
@@ -49,7 +59,7 @@ __device__ __forceinline__ void bn_coeffs(const float* sum, const float* sumsq, 
 struct BnApplyArgs {
   const __nv_bfloat16* y;
   const float *sum, *sumsq, *gamma, *beta;
-  const __nv_bfloat16* res;  // optional second operand of the residual add
+  const __nv_bfloat16* res;                     // optional second operand of the residual add
   const float *rsum, *rsumsq, *rgamma, *rbeta;  // if non-null, res is a raw conv output with its own BN
   __nv_bfloat16* out;
   float *mean_out, *invstd_out, *running_mean, *running_var;
@@ -81,7 +91,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int rows_per_block = 256 / tpr;
   const int cg = threadIdx.x % tpr;
   const int roff = threadIdx.x / tpr;
-  if (roff >= rows_per_block) return;
   const int c0 = cg * 8;
   const float inv_m = 1.f / (float)a.M;
   float mean[8], invstd[8], scale[8], shift[8];
@@ -92,7 +101,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     shift[i] = a.beta[c0 + i] - mean[i] * scale[i];
   }
   float rscale[8], rshift[8];
-  const bool res_bn = a.res != nullptr && a.rsum != nullptr;
+  const bool has_res = a.res != nullptr;
+  const bool res_bn = has_res && a.rsum != nullptr;
   if (res_bn) {
     float rmean[8], rinvstd[8];
     bn_coeffs(a.rsum, a.rsumsq, c0, inv_m, a.eps, rmean, rinvstd);
@@ -104,149 +114,160 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     if (blockIdx.x == 0 && roff == 0)
       bn_bookkeeping(rmean, rinvstd, c0, a.M, a.eps, a.momentum, a.rmean_out, a.rinvstd_out, a.rrunning_mean,
                      a.rrunning_var);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rscale[i] = 1.f, rshift[i] = 0.f;
   }
   if (blockIdx.x == 0 && roff == 0)
     bn_bookkeeping(mean, invstd, c0, a.M, a.eps, a.momentum, a.mean_out, a.invstd_out, a.running_mean, a.running_var);
 
-  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M;
-       r += (long long)gridDim.x * rows_per_block) {
-    const long long off = r * a.C + c0;
-    float v[8];
-    unpack8(ld8(a.y + off), v);
+  const long long stride = (long long)gridDim.x * rows_per_block;
+  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M; r += kRows * stride) {
+    bf16x8 yv[kRows], rv[kRows];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], scale[i], shift[i]);
-    if (a.res) {
-      float rv[8];
-      unpack8(ld8(a.res + off), rv);
-      if (res_bn) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += fmaf(rv[i], rscale[i], rshift[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    for (int j = 0; j < kRows; ++j) {
+      const long long rr = r + j * stride;
+      if (rr < a.M) {
+        yv[j] = ld8(a.y + rr * a.C + c0);
+        if (has_res) rv[j] = ld8(a.res + rr * a.C + c0);
       }
     }
-    if (a.relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int j = 0; j < kRows; ++j) {
+      const long long rr = r + j * stride;
+      if (rr >= a.M) break;
+      float v[8];
+      unpack8(yv[j], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], scale[i], shift[i]);
+      if (has_res) {
+        float q[8];
+        unpack8(rv[j], q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += fmaf(q[i], rscale[i], rshift[i]);
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      st8(a.out + rr * a.C + c0, pack8(v));
     }
-    st8(a.out + off, pack8(v));
   }
 }
 
-// ---- BatchNorm backward, pass 1: per-channel sum(g) and sum(g * xhat), g = dout * [mask > 0] -------
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout,
-                                                            const __nv_bfloat16* __restrict__ mask,
-                                                            const __nv_bfloat16* __restrict__ y,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, float* scratch,
-                                                            long long M, int C) {
-  __shared__ float red[2][256][9];
-  const int tpr = C >> 3;
+// ---- BatchNorm backward ---------------------------------------------------------------------------
+// g = dout * relu'(.) where the ReLU mask comes from (mask_mode)
+//   0: nothing (dout is already masked)        1: a stored activation tensor (mask > 0)
+//   2: recomputed from y: fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0  (no extra HBM read)
+struct BnBwdArgs {
+  const __nv_bfloat16 *dout, *mask, *y;
+  const float *mean, *invstd, *gamma, *beta;
+  float* scratch;          // [2C]: sum g, sum g*xhat
+  __nv_bfloat16 *dy, *g_out;
+  float *dgamma, *dbeta;
+  long long M;
+  int C, mask_mode;
+};
+
+template <bool kApply>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
+  __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][kApply ? 1 : 9];
+  const int tpr = a.C >> 3;
   const int rows_per_block = 256 / tpr;
   const int cg = threadIdx.x % tpr;
   const int roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
-  float s[8], d[8], mu[8], is[8];
+  float mu[8], is[8], scale[8], shift[8], k1[8], k2[8], k3[8], s[8], d[8];
+  const float inv_m = 1.f / (float)a.M;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = d[i] = 0.f, mu[i] = mean[c0 + i], is[i] = invstd[c0 + i];
-  if (roff < rows_per_block) {
-    for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < M;
-         r += (long long)gridDim.x * rows_per_block) {
-      const long long off = r * C + c0;
-      float g[8], yv[8];
-      unpack8(ld8(dout + off), g);
-      unpack8(ld8(y + off), yv);
-      if (mask) {
-        float mv[8];
-        unpack8(ld8(mask + off), mv);
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = a.mean[c0 + i];
+    is[i] = a.invstd[c0 + i];
+    const float gm = a.gamma[c0 + i];
+    scale[i] = gm * is[i];
+    shift[i] = (a.mask_mode == 2 ? a.beta[c0 + i] : 0.f) - mu[i] * scale[i];
+    s[i] = d[i] = 0.f;
+    if (kApply) {
+      const float sg = a.scratch[c0 + i], sgx = a.scratch[a.C + c0 + i];
+      k1[i] = scale[i];
+      k2[i] = sg * inv_m;
+      k3[i] = sgx * inv_m;
+      if (blockIdx.x == 0 && roff == 0) {
+        a.dbeta[c0 + i] += sg;
+        a.dgamma[c0 + i] += sgx;
+      }
+    }
+  }
+  const long long stride = (long long)gridDim.x * rows_per_block;
+  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M; r += kRows * stride) {
+    bf16x8 gv[kRows], yv[kRows], mv[kRows];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = mv[i] > 0.f ? g[i] : 0.f;
+    for (int j = 0; j < kRows; ++j) {
+      const long long rr = r + j * stride;
+      if (rr < a.M) {
+        gv[j] = ld8(a.dout + rr * a.C + c0);
+        yv[j] = ld8(a.y + rr * a.C + c0);
+        if (a.mask_mode == 1) mv[j] = ld8(a.mask + rr * a.C + c0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      const long long rr = r + j * stride;
+      if (rr >= a.M) break;
+      float g[8], yf[8];
+      unpack8(gv[j], g);
+      unpack8(yv[j], yf);
+      if (a.mask_mode == 1) {
+        float m[8];
+        unpack8(mv[j], m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = m[i] > 0.f ? g[i] : 0.f;
+      } else if (a.mask_mode == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(yf[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
+      }
+      if (kApply) {
+        if (a.g_out) st8(a.g_out + rr * a.C + c0, pack8(g));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = k1[i] * (g[i] - k2[i] - (yf[i] - mu[i]) * is[i] * k3[i]);
+        st8(a.dy + rr * a.C + c0, pack8(g));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += g[i];
+          d[i] = fmaf(g[i], (yf[i] - mu[i]) * is[i], d[i]);
+        }
+      }
+    }
+  }
+  if (!kApply) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
+    __syncthreads();
+    if (roff == 0) {
+      for (int rr = 1; rr < rows_per_block; ++rr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += red[0][rr * tpr + cg][i], d[i] += red[1][rr * tpr + cg][i];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        s[i] += g[i];
-        d[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], d[i]);
+        red_add_f32(a.scratch + c0 + i, s[i]);
+        red_add_f32(a.scratch + a.C + c0 + i, d[i]);
       }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
-  __syncthreads();
-  if (roff == 0) {
-    for (int rr = 1; rr < rows_per_block; ++rr) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] += red[0][rr * tpr + cg][i], d[i] += red[1][rr * tpr + cg][i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red_add_f32(scratch + c0 + i, s[i]);
-      red_add_f32(scratch + C + c0 + i, d[i]);
-    }
-  }
-}
-
-// ---- pass 2: dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)) ----------------------------
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout,
-                                                           const __nv_bfloat16* __restrict__ mask,
-                                                           const __nv_bfloat16* __restrict__ y,
-                                                           const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd,
-                                                           const float* __restrict__ gamma,
-                                                           const float* __restrict__ scratch, __nv_bfloat16* dy,
-                                                           __nv_bfloat16* g_out, float* dgamma, float* dbeta,
-                                                           long long M, int C) {
-  const int tpr = C >> 3;
-  const int rows_per_block = 256 / tpr;
-  const int cg = threadIdx.x % tpr;
-  const int roff = threadIdx.x / tpr;
-  if (roff >= rows_per_block) return;
-  const int c0 = cg * 8;
-  const float inv_m = 1.f / (float)M;
-  float mu[8], is[8], k1[8], k2[8], k3[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    mu[i] = mean[c0 + i];
-    is[i] = invstd[c0 + i];
-    const float sg = scratch[c0 + i], sgx = scratch[C + c0 + i];
-    k1[i] = gamma[c0 + i] * is[i];
-    k2[i] = sg * inv_m;
-    k3[i] = sgx * inv_m;
-    if (blockIdx.x == 0 && roff == 0) {
-      dbeta[c0 + i] += sg;
-      dgamma[c0 + i] += sgx;
-    }
-  }
-  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < M;
-       r += (long long)gridDim.x * rows_per_block) {
-    const long long off = r * C + c0;
-    float g[8], yv[8];
-    unpack8(ld8(dout + off), g);
-    unpack8(ld8(y + off), yv);
-    if (mask) {
-      float mv[8];
-      unpack8(ld8(mask + off), mv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = mv[i] > 0.f ? g[i] : 0.f;
-    }
-    if (g_out) st8(g_out + off, pack8(g));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (yv[i] - mu[i]) * is[i];
-      g[i] = k1[i] * (g[i] - k2[i] - xh * k3[i]);
-    }
-    st8(dy + off, pack8(g));
   }
 }
 
 // ---- stem: a = maxpool3x3/s2/p1(relu(bn(y))), y [N][H][W][64] -> a [N][H/2][W/2][64] ----------------
+// also records, per output element, which of the 9 window positions won (first maximum in scan order, as
+// ATen does) so the backward pass is a cheap gather.
 __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y,
                                                                 const float* sum, const float* sumsq,
                                                                 const float* gamma, const float* beta,
-                                                                __nv_bfloat16* out, float* mean_out,
-                                                                float* invstd_out, float* running_mean,
-                                                                float* running_var, int N, int H, int W, float eps,
-                                                                float momentum) {
+                                                                __nv_bfloat16* out, uint8_t* idx_out,
+                                                                float* mean_out, float* invstd_out,
+                                                                float* running_mean, float* running_var, int N,
+                                                                int H, int W, float eps, float momentum) {
   const int C = 64, tpr = 8;
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
@@ -266,29 +287,43 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
     const int wo = (int)(r % Wo);
     const int ho = (int)((r / Wo) % Ho);
     const long long n = r / ((long long)Wo * Ho);
+    bf16x8 win[9];
+    bool ok[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int h = 2 * ho + k / 3 - 1, w = 2 * wo + k % 3 - 1;
+      ok[k] = h >= 0 && h < H && w >= 0 && w < W;
+      if (ok[k]) win[k] = ld8_cached(y + ((n * H + h) * W + w) * C + c0);
+    }
     float best[8];
+    uint32_t bidx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) best[i] = 0.f;  // relu output >= 0 and every window has >= 1 valid pixel
-    for (int dh = -1; dh <= 1; ++dh) {
-      const int h = 2 * ho + dh;
-      if (h < 0 || h >= H) continue;
-      for (int dw = -1; dw <= 1; ++dw) {
-        const int w = 2 * wo + dw;
-        if (w < 0 || w >= W) continue;
-        float v[8];
-        unpack8(ld8(y + ((n * H + h) * W + w) * C + c0), v);
+    for (int i = 0; i < 8; ++i) best[i] = -1.f, bidx[i] = 0;  // relu output >= 0 > -1
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], fmaf(v[i], scale[i], shift[i]));
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      float v[8];
+      unpack8(win[k], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float act = fmaxf(fmaf(v[i], scale[i], shift[i]), 0.f);
+        if (act > best[i]) best[i] = act, bidx[i] = k;
       }
     }
     st8(out + r * C + c0, pack8(best));
+    if (idx_out) {
+      uint2 packed;
+      packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(idx_out + r * C + c0) = packed;
+    }
   }
 }
 
-// backward of the above up to (and excluding) the BN-backward apply: g[pixel] = sum over the pooling
-// windows that selected this pixel (first maximum in scan order, as ATen does) of dpool, times relu';
-// also accumulates the BN-backward sums.
+// backward of the above up to (and excluding) the BN-backward apply: g[pixel] = relu'(.) * sum of dpool over the
+// (at most 4) windows whose recorded winner is this pixel; also accumulates the BN-backward sums.
 __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool,
+                                                            const uint8_t* __restrict__ idx,
                                                             const __nv_bfloat16* __restrict__ y,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
@@ -314,44 +349,44 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
     const int w = (int)(r % W);
     const int h = (int)((r / W) % H);
     const long long n = r / ((long long)W * H);
-    float yv[8], a[8], g[8];
-    unpack8(ld8(y + r * C + c0), yv);
+    const bf16x8 yraw = ld8(y + r * C + c0);
+    // windows (ho, wo) with 2ho-1 <= h <= 2ho+1: ho in {h>>1, (h+1)>>1}
+    bf16x8 dp[4];
+    uint2 wi[4];
+    int kpos[4];
+    bool ok[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = fmaxf(fmaf(yv[i], scale[i], shift[i]), 0.f), g[i] = 0.f;
-    // windows (ho, wo) with 2ho-1 <= h <= 2ho+1
-    for (int ho = (h >> 1); ho <= ((h + 1) >> 1); ++ho) {
-      if (ho >= Ho) continue;
-      for (int wo = (w >> 1); wo <= ((w + 1) >> 1); ++wo) {
-        if (wo >= Wo) continue;
-        // is (h, w) the first maximum of window (ho, wo)?
-        bool sel[8];
+    for (int q = 0; q < 4; ++q) {
+      const int ho = (q >> 1) ? ((h + 1) >> 1) : (h >> 1);
+      const int wo = (q & 1) ? ((w + 1) >> 1) : (w >> 1);
+      // odd h / w belong to two windows, even ones to a single window
+      ok[q] = ho < Ho && wo < Wo && !((q >> 1) && !(h & 1)) && !((q & 1) && !(w & 1));
+      kpos[q] = (h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1));
+      if (ok[q]) {
+        const long long o = ((n * Ho + ho) * Wo + wo) * C + c0;
+        dp[q] = ld8_cached(dpool + o);
+        wi[q] = *reinterpret_cast<const uint2*>(idx + o);
+      }
+    }
+    float yv[8], g[8];
+    unpack8(yraw, yv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sel[i] = true;
-        for (int dh = -1; dh <= 1; ++dh) {
-          const int hh = 2 * ho + dh;
-          if (hh < 0 || hh >= H) continue;
-          for (int dw = -1; dw <= 1; ++dw) {
-            const int ww = 2 * wo + dw;
-            if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
-            float ov[8];
-            unpack8(ld8(y + ((n * H + hh) * W + ww) * C + c0), ov);
-            const bool earlier = hh < h || (hh == h && ww < w);
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float o = fmaxf(fmaf(ov[i], scale[i], shift[i]), 0.f);
-              sel[i] = sel[i] && (earlier ? a[i] > o : a[i] >= o);
-            }
-          }
-        }
-        float dp[8];
-        unpack8(ld8(dpool + ((n * Ho + ho) * Wo + wo) * C + c0), dp);
+    for (int q = 0; q < 4; ++q) {
+      if (!ok[q]) continue;
+      float dv[8];
+      unpack8(dp[q], dv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] += sel[i] ? dp[i] : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t word = i < 4 ? wi[q].x : wi[q].y;
+        const int win = (word >> (8 * (i & 3))) & 0xFF;
+        g[i] += win == kpos[q] ? dv[i] : 0.f;
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      g[i] = a[i] > 0.f ? g[i] : 0.f;
+      g[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
       s[i] += g[i];
       d[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], d[i]);
     }
@@ -439,12 +474,21 @@ __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict
   }
 }
 
-static int grid_for(long long work_items, int per_block) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+// grid for a row-walking kernel: enough blocks for `rows` at `rows_per_block * unroll` rows per block
+// iteration, capped at `waves` resident blocks per SM.
+static int grid_for(long long work_items, int per_block, int waves = 8) {
   long long blocks = (work_items + per_block - 1) / per_block;
-  const long long cap = (long long)sms * 8;
+  const long long cap = (long long)num_sms() * waves;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -453,6 +497,7 @@ static int last_error() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
+static bool bad_channels(int C) { return C % 8 || C > 2048 || C < 8 || (256 % (C / 8)) != 0; }
 
 }  // namespace peclr
 
@@ -465,57 +510,61 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
                               float* running_mean, float* running_var, float* rmean_out, float* rinvstd_out,
                               float* rrunning_mean, float* rrunning_var, long long M, int C, float eps, float momentum,
                               int relu, void* stream) {
-  if (C % 8 || C > 2048 || C < 8 || (256 % (C / 8)) != 0) return -1001;
+  if (bad_channels(C)) return -1001;
   BnApplyArgs a{(const bf16*)y, sum,      sumsq,      gamma,        beta,         (const bf16*)res, rsum,
                 rsumsq,         rgamma,   rbeta,      (bf16*)out,   mean_out,     invstd_out,       running_mean,
                 running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
                 eps,            momentum, relu};
   const int rows_per_block = 256 / (C / 8);
-  bn_apply_kernel<<<grid_for(M, rows_per_block * 4), 256, 0, (cudaStream_t)stream>>>(a);
+  bn_apply_kernel<<<grid_for(M, rows_per_block * kRows), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
 extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean,
-                                   const float* invstd, float* scratch, long long M, int C, void* stream) {
-  if (C % 8 || C > 2048 || (256 % (C / 8)) != 0) return -1001;
+                                   const float* invstd, const float* gamma, const float* beta, int mask_mode,
+                                   float* scratch, long long M, int C, void* stream) {
+  if (bad_channels(C) || mask_mode < 0 || mask_mode > 2 || (mask_mode == 1 && !mask)) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)C * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
+  BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
+              nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_reduce_kernel<<<grid_for(M, rows_per_block * 8), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, scratch, M, C);
+  bn_bwd_kernel<false><<<grid_for(M, rows_per_block * kRows * 2), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
 extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean,
-                                  const float* invstd, const float* gamma, const float* scratch, void* dy,
-                                  void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream) {
-  if (C % 8 || C > 2048 || (256 % (C / 8)) != 0) return -1001;
+                                  const float* invstd, const float* gamma, const float* beta, int mask_mode,
+                                  const float* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
+                                  long long M, int C, void* stream) {
+  if (bad_channels(C) || mask_mode < 0 || mask_mode > 2 || (mask_mode == 1 && !mask)) return -1001;
+  BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
+              (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(M, rows_per_block * 4), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, scratch, (bf16*)dy, (bf16*)g_out,
-      dgamma, dbeta, M, C);
+  bn_bwd_kernel<true><<<grid_for(M, rows_per_block * kRows), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
 extern "C" int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
-                                       const float* beta, void* out, float* mean_out, float* invstd_out,
-                                       float* running_mean, float* running_var, int N, int H, int W, float eps,
-                                       float momentum, void* stream) {
+                                       const float* beta, void* out, void* idx_out, float* mean_out,
+                                       float* invstd_out, float* running_mean, float* running_var, int N, int H,
+                                       int W, float eps, float momentum, void* stream) {
   if ((H & 1) || (W & 1)) return -1001;
-  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2) * (W / 2), 32 * 2), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, mean_out, invstd_out, running_mean, running_var, N, H, W,
-      eps, momentum);
+  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2) * (W / 2), 32), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, (uint8_t*)idx_out, mean_out, invstd_out, running_mean,
+      running_var, N, H, W, eps, momentum);
   return last_error();
 }
 
-extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* y, const float* mean, const float* invstd,
-                                   const float* gamma, const float* beta, void* g_out, float* scratch, int N, int H,
-                                   int W, void* stream) {
-  if ((H & 1) || (W & 1)) return -1001;
+extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, void* g_out,
+                                   float* scratch, int N, int H, int W, void* stream) {
+  if ((H & 1) || (W & 1) || !idx) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * 64 * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
-  stem_pool_bwd_kernel<<<grid_for((long long)N * H * W, 32 * 4), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dpool, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H, W);
+  stem_pool_bwd_kernel<<<grid_for((long long)N * H * W, 32 * 2), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H,
+      W);
   return last_error();
 }
 

@@ -211,10 +211,10 @@ class StepEngine:
         st, sv = slab(64)
         y0 = ops.stem_fprop(xpad, self.w_stem, h, w, stats=st if training else None)
         bn0 = self.stem_bn
-        a, _ = ops.stem_bn_relu_pool(y0, self._bn_stats_for(bn0, n * (h // 2) * (w // 2), training, st),
-                                     self._p(bn0, "weight"), self._p(bn0, "bias"), run(bn0), bn0.eps, bn0.momentum,
-                                     saved=sv)
-        ctx["stem"] = (xpad, y0, sv)
+        a, _, pool_idx = ops.stem_bn_relu_pool(y0, self._bn_stats_for(bn0, n * (h // 2) * (w // 2), training, st),
+                                               self._p(bn0, "weight"), self._p(bn0, "bias"), run(bn0), bn0.eps,
+                                               bn0.momentum, saved=sv, want_idx=training)
+        ctx["stem"] = (xpad, y0, sv, pool_idx)
         hh, ww = h // 4, w // 4
         for blk in self.blocks:
             rec = {"a_in": a, "in_hw": (hh, ww), "convs": []}
@@ -361,8 +361,9 @@ class StepEngine:
                 conv, bn, x, y, act, sv = convs[i]
                 pconv, pbn, px, py, pact, psv = convs[i - 1]
                 dx = ops.conv2d_dgrad(dy, self._wt(conv), tuple(x.shape), conv.k, conv.stride)
-                dy = ops.bn_backward(dx, pact, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
-                                     self._g(pbn, "bias"), scratch=scratch, dy=dx)
+                # inner BN + ReLU: the mask is recomputed from y (no read of the stored activation)
+                dy = ops.bn_backward(dx, None, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
+                                     self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"))
                 ops.conv2d_wgrad(px, dy, pconv.k, pconv.stride, dw=self._g(pconv, "weight"))
             conv1 = convs[0][0]
             if "down" in rec:
@@ -379,10 +380,10 @@ class StepEngine:
             if after_stage is not None and (bi == 0 or stage_of[id(self.blocks[bi - 1])] != stage_of[id(blk)]):
                 after_stage(stage_of[id(blk)])
         # stem: max-pool + ReLU + BN backward, then the 7x7 weight gradient
-        xpad, y0, sv0 = ctx["stem"]
+        xpad, y0, sv0, pool_idx = ctx["stem"]
         h, w = ctx["hw"]
         bn0 = self.stem_bn
-        dy0 = ops.stem_pool_bn_backward(da, y0, sv0, self._p(bn0, "weight"), self._p(bn0, "bias"),
+        dy0 = ops.stem_pool_bn_backward(da, pool_idx, y0, sv0, self._p(bn0, "weight"), self._p(bn0, "bias"),
                                         self._g(bn0, "weight"), self._g(bn0, "bias"), scratch=scratch)
         dwp = ops.stem_wgrad(xpad, dy0, h, w)
         _lib.call("peclr_stem_unpack_grad", dwp, self._g(self.stem_conv, "weight"), ops._s())

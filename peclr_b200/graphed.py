@@ -1,0 +1,52 @@
+"""CUDA-graph capture of one micro-step (training_step + backward) so the ~340 (RN50) / ~950 (RN152) kernel
+launches of a step are submitted with one cudaGraphLaunch instead of one Python -> ctypes call each.
+
+The captured work is exactly what ``model.training_step(batch, i)`` followed by ``(loss * scale).backward()``
+enqueues on the stream; the optimiser step stays outside (its learning rate / step count change per step)."""
+from typing import Dict
+
+import torch
+
+
+class GraphedStep:
+    def __init__(self, model, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0, warmup: int = 2):
+        dev = model.engine.device
+        self.model = model
+        self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        self.grad_scale = grad_scale
+        self.graph = torch.cuda.CUDAGraph()
+        model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # allocator / lazy-init warm-up outside the capture
+                model.train_metrics = {}
+                out = model.training_step(self.static, 0)
+                (out["loss"] * grad_scale).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # the warm-up steps must not leak into the user's gradient / BN state more than a real step would:
+        # callers zero the gradients before the first replay (Trainer and bench do).
+        from . import _lib
+
+        before = _lib.LAUNCHES
+        with torch.cuda.graph(self.graph):
+            model.train_metrics = {}
+            out = model.training_step(self.static, 0)
+            (out["loss"] * grad_scale).backward()
+        self.kernels_per_replay = _lib.LAUNCHES - before
+        self.out = {k: v.detach() for k, v in out.items()}
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Copies the batch into the captured input buffers and replays the step.  The returned tensors are the
+        graph's static outputs (valid until the next replay)."""
+        from . import _lib
+
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        _lib.LAUNCHES += self.kernels_per_replay
+        self.model.train_metrics = dict(self.out)
+        return self.out

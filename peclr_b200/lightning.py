@@ -167,6 +167,7 @@ class Trainer:
         self.optimizers, self.lr_schedulers = opts, scheds
         opt, sched = opts[0], scheds[0]["scheduler"]
         acc = self.accumulate_grad_batches
+        graphed = None
         opt.zero_grad()
         for epoch in range(self.max_epochs):
             self.current_epoch = epoch
@@ -177,10 +178,20 @@ class Trainer:
                 if self.limit_train_batches is not None and batch_idx >= self.limit_train_batches:
                     break
                 batch = self._to_device(batch, device)
-                model.train_metrics = {}
-                out = model.training_step(batch, batch_idx)
-                (out["loss"] / acc).backward()
-                outputs.append({k: v.detach() for k, v in out.items()})
+                if self.use_cuda_graph:
+                    # same work as the eager branch below, submitted as one captured CUDA graph
+                    if graphed is None:
+                        from .graphed import GraphedStep
+
+                        graphed = GraphedStep(model, batch, grad_scale=1.0 / acc)
+                        opt.zero_grad()
+                    out = graphed(batch)
+                    outputs.append({k: v.clone() for k, v in out.items()})
+                else:
+                    model.train_metrics = {}
+                    out = model.training_step(batch, batch_idx)
+                    (out["loss"] / acc).backward()
+                    outputs.append({k: v.detach() for k, v in out.items()})
                 seen += 2 * batch["transformed_image1"].shape[0] * self.world_size
                 if (batch_idx + 1) % acc == 0:
                     model.sync_gradients()

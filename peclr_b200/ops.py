@@ -120,42 +120,48 @@ def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=No
     return (out, saved, rsaved) if res_bn is not None else (out, saved)
 
 
-def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratch=None, dy=None, g_out=None):
-    """BatchNorm(+ReLU mask) backward.  dgamma/dbeta are accumulated in place.  Returns dy[, g]."""
+def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratch=None, dy=None, g_out=None,
+                beta=None):
+    """BatchNorm(+ReLU) backward.  ReLU mask: `mask` tensor (activation > 0) if given, else recomputed from y when
+    `beta` is given, else none (dout already masked).  dgamma/dbeta are accumulated in place.  Returns dy[, g]."""
     c = y.shape[-1]
     m = y.numel() // c
+    mode = 1 if mask is not None else (2 if beta is not None else 0)
     if scratch is None:
         scratch = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
     dy = dy if dy is not None else torch.empty_like(y)
     if want_g and g_out is None:
         g_out = torch.empty_like(y)
-    _lib.call("peclr_bn_bwd_reduce", dout, mask, y, saved[0], saved[1], scratch, m, c, _s())
-    _lib.call("peclr_bn_bwd_apply", dout, mask, y, saved[0], saved[1], gamma, scratch, dy, g_out, dgamma, dbeta,
-              m, c, _s())
+    _lib.call("peclr_bn_bwd_reduce", dout, mask, y, saved[0], saved[1], gamma, beta, mode, scratch, m, c, _s())
+    _lib.call("peclr_bn_bwd_apply", dout, mask, y, saved[0], saved[1], gamma, beta, mode, scratch, dy, g_out,
+              dgamma, dbeta, m, c, _s())
     return (dy, g_out) if want_g else dy
 
 
-def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.1, out=None, saved=None):
+def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.1, out=None, saved=None,
+                      want_idx=True):
+    """Returns pooled activation, saved (mean, invstd), idx (uint8 winners, or None)."""
     n, h, w, c = y.shape
     assert c == 64
     out = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=y.device)
+    idx = torch.empty((n, h // 2, w // 2, 64), dtype=torch.uint8, device=y.device) if want_idx else None
     if saved is None:
         saved = torch.empty((2, 64), dtype=torch.float32, device=y.device)
-    _lib.call("peclr_stem_bn_relu_pool", y, stats[0], stats[1], gamma, beta, out, saved[0], saved[1],
+    _lib.call("peclr_stem_bn_relu_pool", y, stats[0], stats[1], gamma, beta, out, idx, saved[0], saved[1],
               running[0] if running is not None else None, running[1] if running is not None else None,
               n, h, w, eps, momentum, _s())
-    return out, saved
+    return out, saved, idx
 
 
-def stem_pool_bn_backward(dpool, y, saved, gamma, beta, dgamma, dbeta, g_buf=None, scratch=None):
+def stem_pool_bn_backward(dpool, idx, y, saved, gamma, beta, dgamma, dbeta, g_buf=None, scratch=None):
     """Backward through maxpool + relu + stem BN.  Returns dy (grad of the raw stem conv output)."""
     n, h, w, c = y.shape
     if scratch is None:
         scratch = torch.empty((128,), dtype=torch.float32, device=y.device)
     g = g_buf if g_buf is not None else torch.empty_like(y)
-    _lib.call("peclr_stem_pool_bwd", dpool, y, saved[0], saved[1], gamma, beta, g, scratch, n, h, w, _s())
+    _lib.call("peclr_stem_pool_bwd", dpool, idx, y, saved[0], saved[1], gamma, beta, g, scratch, n, h, w, _s())
     # pass 2: plain BN backward apply on the already masked gradient (in place: dy overwrites g)
-    _lib.call("peclr_bn_bwd_apply", g, None, y, saved[0], saved[1], gamma, scratch, g, None, dgamma, dbeta,
+    _lib.call("peclr_bn_bwd_apply", g, None, y, saved[0], saved[1], gamma, None, 0, scratch, g, None, dgamma, dbeta,
               n * h * w, 64, _s())
     return g
 

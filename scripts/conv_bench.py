@@ -1,0 +1,69 @@
+"""Per-shape timing of the tensor-core conv kernels on the 23 ResNet-50/152 shapes at
+2B = 256 images: milliseconds, TFLOP/s and algorithmic GB/s for fprop / dgrad / wgrad.  GPU only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from peclr_b200 import ops  # noqa: E402
+
+SHAPES = [  # Cin, Hin, Cout, k, s, count50, count152
+    (64, 56, 64, 1, 1, 1, 1), (64, 56, 64, 3, 1, 3, 3), (64, 56, 256, 1, 1, 4, 4), (256, 56, 64, 1, 1, 2, 2),
+    (256, 56, 128, 1, 1, 1, 1), (128, 56, 128, 3, 2, 1, 1), (128, 28, 512, 1, 1, 4, 8), (256, 56, 512, 1, 2, 1, 1),
+    (512, 28, 128, 1, 1, 3, 7), (128, 28, 128, 3, 1, 3, 7), (512, 28, 256, 1, 1, 1, 1), (256, 28, 256, 3, 2, 1, 1),
+    (256, 14, 1024, 1, 1, 6, 36), (512, 28, 1024, 1, 2, 1, 1), (1024, 14, 256, 1, 1, 5, 35), (256, 14, 256, 3, 1, 5, 35),
+    (1024, 14, 512, 1, 1, 1, 1), (512, 14, 512, 3, 2, 1, 1), (512, 7, 2048, 1, 1, 3, 3), (1024, 14, 2048, 1, 2, 1, 1),
+    (2048, 7, 512, 1, 1, 2, 2), (512, 7, 512, 3, 1, 2, 2),
+]
+
+
+def timeit(fn, reps=5):
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()  # evict L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    tot = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
+    print("%-28s %9s %7s %7s | %9s %7s | %9s %7s" % ("shape", "fprop ms", "TF/s", "GB/s", "dgrad ms", "TF/s", "wgrad ms", "TF/s"))
+    for cin, h, cout, k, s, c50, c152 in SHAPES:
+        x = torch.randn(n, h, h, cin, device="cuda").bfloat16()
+        w = (torch.randn(cout, k * k, cin, device="cuda") / (cin * k * k) ** 0.5).bfloat16()
+        wt = w.permute(2, 1, 0).contiguous()
+        ho = h // s
+        dy = torch.randn(n, ho, ho, cout, device="cuda").bfloat16()
+        y = torch.empty(n, ho, ho, cout, device="cuda", dtype=torch.bfloat16)
+        dx = torch.empty_like(x)
+        dw = torch.zeros(cout, k * k, cin, device="cuda")
+        stats = torch.zeros(2, cout, device="cuda")
+        flops = 2.0 * n * ho * ho * cout * cin * k * k
+        t_f = timeit(lambda: ops.conv2d_fprop(x, w, k, s, out=y, stats=stats))
+        t_d = timeit(lambda: ops.conv2d_dgrad(dy, wt, tuple(x.shape), k, s, out=dx))
+        t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, k, s, dw=dw))
+        gb = (x.numel() + y.numel() + w.numel()) * 2 / 1e9
+        name = "%dx%d %d->%d k%d s%d" % (h, h, cin, cout, k, s)
+        print("%-28s %9.3f %7.1f %7.0f | %9.3f %7.1f | %9.3f %7.1f" % (
+            name, t_f, flops / t_f / 1e9, gb / t_f * 1e3, t_d, flops / t_d / 1e9, t_w, flops / t_w / 1e9))
+        for key, t in (("fprop", t_f), ("dgrad", t_d), ("wgrad", t_w)):
+            tot[key][0] += t * c50
+            tot[key][1] += t * c152
+    print("weighted by layer count (ms per step, excluding stem):")
+    for key, (a, b) in tot.items():
+        print("  %-6s RN50 %.2f ms   RN152 %.2f ms" % (key, a, b))
+
+
+if __name__ == "__main__":
+    main()

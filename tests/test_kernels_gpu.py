@@ -169,6 +169,13 @@ def test_bn_apply_and_backward(ops, c, m):
     assert rel_l2(dy.float().view(m, c), yt.grad) < 1e-2
     assert rel_l2(dgamma, gt.grad) < 2e-3 and rel_l2(dbeta, bt.grad) < 2e-3
     assert torch.equal(gout.float().view(m, c), dout.float() * mask)
+    # mask recomputed from y (no residual): compare against torch's relu(bn(y)) backward
+    yt2 = yf.clone().requires_grad_()
+    torch.relu(F.batch_norm(yt2, None, None, gamma, beta, training=True, eps=1e-5)).backward(dout.float())
+    dg2, db2 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dy2 = ops.bn_backward(dout.view(m, 1, 1, c), None, y.view(m, 1, 1, c), saved, gamma, dg2, db2, beta=beta)
+    torch.cuda.synchronize()
+    assert rel_l2(dy2.float().view(m, c), yt2.grad) < 1e-2
 
 
 def test_bn_apply_downsample_branch(ops):
@@ -197,7 +204,7 @@ def test_stem_bn_relu_pool_fwd_bwd(ops, n, hw):
     beta = torch.randn(64, device="cuda", generator=g) * 0.3
     yf = y.float().reshape(-1, 64)
     stats = torch.stack([yf.sum(0), (yf * yf).sum(0)])
-    out, saved = ops.stem_bn_relu_pool(y, stats, gamma, beta)
+    out, saved, idx = ops.stem_bn_relu_pool(y, stats, gamma, beta)
     yt = y.float().permute(0, 3, 1, 2).clone().requires_grad_()
     gt, bt = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
     a = torch.relu(F.batch_norm(yt, None, None, gt, bt, training=True, eps=1e-5))
@@ -207,7 +214,7 @@ def test_stem_bn_relu_pool_fwd_bwd(ops, n, hw):
     dpool = torch.randn(n, hw // 2, hw // 2, 64, device="cuda", generator=g).bfloat16()
     ref.backward(dpool.float().permute(0, 3, 1, 2))
     dgamma, dbeta = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
-    dy = ops.stem_pool_bn_backward(dpool, y, saved, gamma, beta, dgamma, dbeta)
+    dy = ops.stem_pool_bn_backward(dpool, idx, y, saved, gamma, beta, dgamma, dbeta)
     torch.cuda.synchronize()
     assert rel_l2(dy.permute(0, 3, 1, 2).float(), yt.grad) < 2e-2
     assert rel_l2(dgamma, gt.grad) < 1e-2 and rel_l2(dbeta, bt.grad) < 1e-2
