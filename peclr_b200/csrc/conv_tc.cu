@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
+    const uint32_t sD32 = smem_u32(sD), sStat32 = smem_u32(sStat);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        uint8_t* box = sD + (chunk >> 1) * kStageA + row * 128;
+        const uint32_t box = sD32 + (chunk >> 1) * kStageA + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c16 = (chunk & 1) * 4 + j;  // 16-byte chunk inside the 128-byte row
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
           v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
           v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
           v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-          *reinterpret_cast<uint4*>(box + ((c16 ^ (row & 7)) << 4)) = v;
+          sts_v4(box + ((c16 ^ (row & 7)) << 4), v);
         }
       }
       tc_fence_before();
@@ -207,47 +208,46 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         tma_commit_group();
       }
       if (want_stats) {
-        // column sums of the bf16 values just staged (exactly what the next kernels will read)
+        // column sums of the bf16 values just staged (exactly what the next kernels will read).  Thread =
+        // one column pair x one contiguous row range; shared-space 32-bit loads, 8 rows in flight.
         constexpr int kPairs = BN / 2;
         constexpr int kRowGroups = 128 / kPairs > 0 ? 128 / kPairs : 1;
+        constexpr int kRowsPer = 128 / kRowGroups;
         const int pair = et % kPairs;
         const int rg = et / kPairs;
         const int col = pair * 2;
-        const uint8_t* base = sD + (col >> 6) * kStageA + ((col & 7) << 1);
         const int c16 = (col & 63) >> 3;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        if (rg < kRowGroups) {
-          // rows of a box that hangs over the image edge are clipped by the TMA store: keep them out of
-          // the statistics too (their taps can still reach valid pixels, so they are not zero)
-          const bool edge = w0 + p.Wb > p.d_w || h0 + p.Hb > p.d_h || n0 + p.Nb > p.d_n;
-          if (!edge) {
-#pragma unroll 4
-            for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
-              const float a = bf16_lo(v), b = bf16_hi(v);
-              s0 += a;
-              s1 += b;
-              q0 = fmaf(a, a, q0);
-              q1 = fmaf(b, b, q1);
-            }
-          } else {
-            for (int r0 = rg; r0 < 128; r0 += kRowGroups) {
+        const uint32_t base = sD32 + (col >> 6) * kStageA + ((col & 7) << 1) + rg * kRowsPer * 128;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
+        // rows of a box that hangs over the image edge are clipped by the TMA store: keep them out of the
+        // statistics too (their taps can still reach valid pixels, so they are not zero)
+        const bool edge = w0 + p.Wb > p.d_w || h0 + p.Hb > p.d_h || n0 + p.Nb > p.d_n;
+#pragma unroll 2
+        for (int r8 = 0; r8 < kRowsPer / 8; ++r8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = lds_u32(base + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
+          if (edge) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r0 = rg * kRowsPer + r8 * 8 + j;
               const int wl = r0 & (p.Wb - 1), hl = (r0 >> p.log_wb) & (p.Hb - 1), nl = r0 >> p.log_wbhb;
-              if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) continue;
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
-              const float a = bf16_lo(v), b = bf16_hi(v);
-              s0 += a;
-              s1 += b;
-              q0 = fmaf(a, a, q0);
-              q1 = fmaf(b, b, q1);
+              if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) v[j] = 0u;
             }
           }
-          float* ss = sStat + nt * BN + col;
-          atomicAdd(ss, s0);
-          atomicAdd(ss + 1, s1);
-          atomicAdd(ss + p.cout, q0);
-          atomicAdd(ss + p.cout + 1, q1);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float a0 = bf16_lo(v[j]), b0 = bf16_hi(v[j]);
+            const float a1 = bf16_lo(v[j + 1]), b1 = bf16_hi(v[j + 1]);
+            s0 += a0, s1 += b0, s2 += a1, s3 += b1;
+            q0 = fmaf(a0, a0, q0), q1 = fmaf(b0, b0, q1), q2 = fmaf(a1, a1, q2), q3 = fmaf(b1, b1, q3);
+          }
         }
+        const uint32_t ss = sStat32 + (nt * BN + col) * 4;
+        red_shared_add_f32(ss, s0 + s2);
+        red_shared_add_f32(ss + 4, s1 + s3);
+        red_shared_add_f32(ss + p.cout * 4, q0 + q2);
+        red_shared_add_f32(ss + p.cout * 4 + 4, q1 + q3);
       }
     }
     if (et == 0) tma_wait_group0();

@@ -20,9 +20,7 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # allocator / lazy-init warm-up outside the capture
-                model.train_metrics = {}
-                out = model.training_step(self.static, 0)
-                (out["loss"] * grad_scale).backward()
+                out = model.forward_backward(self.static, grad_scale)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # the warm-up steps must not leak into the user's gradient / BN state more than a real step would:
@@ -31,9 +29,7 @@ class GraphedStep:
 
         before = _lib.LAUNCHES
         with torch.cuda.graph(self.graph):
-            model.train_metrics = {}
-            out = model.training_step(self.static, 0)
-            (out["loss"] * grad_scale).backward()
+            out = model.forward_backward(self.static, grad_scale)
         self.kernels_per_replay = _lib.LAUNCHES - before
         self.out = {k: v.detach() for k, v in out.items()}
 

@@ -50,11 +50,11 @@ class SimCLR(BaseModel):
         )
 
     # ---- the step --------------------------------------------------------------------------------------
-    def _run_step(self, batch: Dict[str, Tensor], want_stats: bool):
+    def _forward(self, batch: Dict[str, Tensor], want_grad: bool):
+        """trunk -> head -> fused loss kernel.  Returns loss [1], stats [16], g_p (dloss/dp or None), contexts."""
         eng = self.engine
         img1, img2 = batch["transformed_image1"], batch["transformed_image2"]
         training = self.training
-        want_grad = training and torch.is_grad_enabled()
         enc, trunk_ctx = eng.forward_trunk(img1.contiguous(), img2.contiguous(), training=training)
         p, head_ctx = eng.forward_head(enc, training=training)
         aug = self.config.augmentation if self.uses_equivariance else []
@@ -67,6 +67,11 @@ class SimCLR(BaseModel):
             angle = torch.cat((batch["angle_1"], batch["angle_2"])).to(torch.float64)
         loss, stats, g_p = eng.forward_loss(p, angle, jx, jy, tuple(img1.shape[-2:]), crop, rotate,
                                             temperature=0.5, want_grad=want_grad)
+        return loss, stats, g_p, head_ctx, trunk_ctx
+
+    def _run_step(self, batch: Dict[str, Tensor], want_stats: bool):
+        want_grad = self.training and torch.is_grad_enabled()
+        loss, stats, g_p, head_ctx, trunk_ctx = self._forward(batch, want_grad)
         if want_grad:
             if self._anchor is None or self._anchor.device != loss.device:
                 self._anchor = torch.zeros((), device=loss.device, requires_grad=True)
@@ -74,6 +79,22 @@ class SimCLR(BaseModel):
         else:
             loss = loss.reshape(())
         return loss, stats
+
+    def forward_backward(self, batch: Dict[str, Tensor], grad_scale: float = 1.0) -> Dict[str, Tensor]:
+        """training_step + (loss * grad_scale).backward() without going through autograd: the same kernels in
+        the same order, enqueued directly (this is what the CUDA-graph capture records).  Gradients accumulate
+        into the flat buffer every parameter's .grad is a view of.  Returns the metric dict (detached)."""
+        with torch.no_grad():
+            loss, stats, g_p, head_ctx, trunk_ctx = self._forward(batch, want_grad=True)
+            if grad_scale != 1.0:
+                g_p = g_p * grad_scale
+            d_enc = self.engine.backward_head(g_p, head_ctx)
+            self.engine.backward_trunk(d_enc, trunk_ctx, after_stage=self._after_stage_hook)
+        out = {"loss": loss.reshape(())}
+        if self.uses_equivariance:
+            out.update({name: stats[i] for i, name in enumerate(STAT_NAMES)})
+        self.train_metrics = {**self.train_metrics, **out}
+        return out
 
     def contrastive_step(self, batch: Dict[str, Tensor]) -> Tensor:
         loss, _ = self._run_step(batch, want_stats=False)

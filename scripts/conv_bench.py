@@ -39,7 +39,10 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     tot = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
     print("%-28s %9s %7s %7s | %9s %7s | %9s %7s" % ("shape", "fprop ms", "TF/s", "GB/s", "dgrad ms", "TF/s", "wgrad ms", "TF/s"))
-    for cin, h, cout, k, s, c50, c152 in SHAPES:
+    only = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
+    for si, (cin, h, cout, k, s, c50, c152) in enumerate(SHAPES):
+        if only is not None and si not in only:
+            continue
         x = torch.randn(n, h, h, cin, device="cuda").bfloat16()
         w = (torch.randn(cout, k * k, cin, device="cuda") / (cin * k * k) ** 0.5).bfloat16()
         wt = w.permute(2, 1, 0).contiguous()
@@ -51,12 +54,13 @@ def main():
         stats = torch.zeros(2, cout, device="cuda")
         flops = 2.0 * n * ho * ho * cout * cin * k * k
         t_f = timeit(lambda: ops.conv2d_fprop(x, w, k, s, out=y, stats=stats))
+        t_n = timeit(lambda: ops.conv2d_fprop(x, w, k, s, out=y))
         t_d = timeit(lambda: ops.conv2d_dgrad(dy, wt, tuple(x.shape), k, s, out=dx))
         t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, k, s, dw=dw))
         gb = (x.numel() + y.numel() + w.numel()) * 2 / 1e9
         name = "%dx%d %d->%d k%d s%d" % (h, h, cin, cout, k, s)
-        print("%-28s %9.3f %7.1f %7.0f | %9.3f %7.1f | %9.3f %7.1f" % (
-            name, t_f, flops / t_f / 1e9, gb / t_f * 1e3, t_d, flops / t_d / 1e9, t_w, flops / t_w / 1e9))
+        print("%-28s %9.3f %7.1f %7.0f | %9.3f %7.1f | %9.3f %7.1f | nostats %.3f" % (
+            name, t_f, flops / t_f / 1e9, gb / t_f * 1e3, t_d, flops / t_d / 1e9, t_w, flops / t_w / 1e9, t_n))
         for key, t in (("fprop", t_f), ("dgrad", t_d), ("wgrad", t_w)):
             tot[key][0] += t * c50
             tot[key][1] += t * c152
