@@ -487,6 +487,12 @@ static int num_sms() {
 // grid for a row-walking kernel: enough blocks for `rows` at `rows_per_block * unroll` rows per block
 // iteration, capped at `waves` resident blocks per SM.
 static int grid_for(long long work_items, int per_block, int waves = 8) {
+  static int env_waves = -1;  // tuning knob: PECLR_ELT_WAVES overrides the resident-blocks-per-SM cap
+  if (env_waves < 0) {
+    const char* e = getenv("PECLR_ELT_WAVES");
+    env_waves = e ? atoi(e) : 0;
+  }
+  if (env_waves > 0) waves = env_waves;
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * waves;
   if (blocks > cap) blocks = cap;
@@ -516,7 +522,7 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
                 running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
                 eps,            momentum, relu};
   const int rows_per_block = 256 / (C / 8);
-  bn_apply_kernel<<<grid_for(M, rows_per_block * kRows), 256, 0, (cudaStream_t)stream>>>(a);
+  bn_apply_kernel<<<grid_for(M, rows_per_block * kRows, 4), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
@@ -529,7 +535,7 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
               nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_kernel<false><<<grid_for(M, rows_per_block * kRows * 2), 256, 0, (cudaStream_t)stream>>>(a);
+  bn_bwd_kernel<false><<<grid_for(M, rows_per_block * kRows * 2, 2), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
@@ -541,7 +547,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
               (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_kernel<true><<<grid_for(M, rows_per_block * kRows), 256, 0, (cudaStream_t)stream>>>(a);
+  bn_bwd_kernel<true><<<grid_for(M, rows_per_block * kRows, 2), 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 

@@ -21,8 +21,8 @@
 //       channels, up to 512/BN taps accumulate side by side in TMEM; split over pixel ranges across
 //       CTAs and reduced with fp32 red.global.add.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
-// epilogue (one TMEM lane quarter each).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), then the epilogue warps (8 in the
+// fprop/dgrad kernel: two per TMEM lane quarter, splitting the columns; 4 in the wgrad kernel).
 #include "conv_tc.h"
 
 #include <stdio.h>
@@ -50,7 +50,7 @@ struct GemmParams {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kStageB = BN * 128;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 128);
+        mbar_init(&tempty[i], 256);
       }
       fence_barrier_init();
     }
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     tmem_alloc<2 * BN>(tmem_slot);
   }
   if (want_stats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 128) sStat[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 256) sStat[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -159,9 +159,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    // 8 epilogue warps: warps w and w + 4 share TMEM lane quarter (w & 3) and split the tile's columns
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int et = threadIdx.x - 64;  // 0..255
     const uint32_t sD32 = smem_u32(sD), sStat32 = smem_u32(sStat);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -175,9 +177,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       if (et == 0) tma_wait_group_read0();  // previous tile's TMA store has finished reading sD
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
 #pragma unroll
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int ci = 0; ci < BN / 64; ++ci) {
+        const int chunk = half * (BN / 64) + ci;
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       tc_fence_before();
       mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (et == 0) {
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         // column sums of the bf16 values just staged (exactly what the next kernels will read).  Thread =
         // one column pair x one contiguous row range; shared-space 32-bit loads, 8 rows in flight.
         constexpr int kPairs = BN / 2;
-        constexpr int kRowGroups = 128 / kPairs > 0 ? 128 / kPairs : 1;
+        constexpr int kRowGroups = 256 / kPairs;
         constexpr int kRowsPer = 128 / kRowGroups;
         const int pair = et % kPairs;
         const int rg = et / kPairs;
@@ -252,8 +255,8 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     }
     if (et == 0) tma_wait_group0();
     if (want_stats) {
-      named_bar_sync(1, 128);
-      for (int i = et; i < p.cout; i += 128) {
+      named_bar_sync(1, 256);
+      for (int i = et; i < p.cout; i += 256) {
         const float s = sStat[i], qq = sStat[p.cout + i];
         if (s != 0.f || qq != 0.f) {
           red_add_f32(p.stat_sum + i, s);
@@ -516,7 +519,7 @@ static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
   if (e != cudaSuccess) return -(int)e;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, 192, smem, stream>>>(p);
+  kern<<<grid, 320, smem, stream>>>(p);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
