@@ -103,14 +103,15 @@ int peclr_colsum_acc(const float* x, float* out, int M, int N, void* stream);
  * loss [1]; stats [16] = proj1 {x_mean,x_median,x_min,x_max,y_mean,y_median,y_min,y_max}, proj2 {...};
  * g_p [2B][128] = dloss/dp (NULL: forward only).  world > 1: the embedding all-gather is fused into
  * the kernel -- z_peers[r] / flag_peers[r] are rank r's z buffer (the start of its workspace) and flag
- * array (unsigned[world]) mapped into this process (symmetric / peer memory); epoch must increase by
- * one per call.  The loss is the GLOBAL-batch mean on every rank and g_p its gradient w.r.t. the local
+ * array (unsigned[world]) mapped into this process (symmetric / peer memory).  The workspace must be zeroed once
+ * before first use; the kernel keeps its launch counter there (flags are tagged with it and the gathered
+ * embeddings are double buffered by its parity), so the call can be captured in a CUDA graph and replayed.  The loss is the GLOBAL-batch mean on every rank and g_p its gradient w.r.t. the local
  * rows, so parameter gradients are SUMMED across ranks. */
 long long peclr_ntxent_workspace_bytes(int B, int world);
 int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx, const long long* jy, int B, int dim,
                        int img_h, int img_w, int crop, int rotate, float temperature, float* loss, float* stats,
                        float* g_p, void* workspace, long long workspace_bytes, int world, int rank,
-                       float* const* z_peers, unsigned* const* flag_peers, unsigned epoch, void* stream);
+                       float* const* z_peers, unsigned* const* flag_peers, void* stream);
 
 /* NT-Xent alone on already-normalised embeddings z [2B][128] (view-1 rows then view-2 rows): the same kernel
  * without the normalisation / correction phases.  Replaces vanila_contrastive_loss (src/models/utils.py:154-186)

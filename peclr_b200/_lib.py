@@ -35,7 +35,7 @@ SIGNATURES = {
     "peclr_bn1d_relu_bwd": [P] * 9 + [I, I, P],
     "peclr_colsum_acc": [P, P, I, I, P],
     "peclr_ntxent_workspace_bytes": [I, I],
-    "peclr_ntxent_fused": [P, P, P, P, I, I, I, I, I, I, F, P, P, P, P, L, I, I, P, P, c_uint, P],
+    "peclr_ntxent_fused": [P, P, P, P, I, I, I, I, I, I, F, P, P, P, P, L, I, I, P, P, P],
     "peclr_ntxent_plain": [P, I, I, F, P, P, P, L, P],
     "peclr_opt_chunk_elems": [],
     "peclr_lars_adam_step": [P, P, P, P, P, P, P, I, P, P, I, P, F, I, F, F, F, I, F, I, F, P],

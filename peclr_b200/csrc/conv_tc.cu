@@ -279,6 +279,7 @@ struct WgradParams {
   CUtensorMap dy_map;
   TapTable taps;
   int num_taps, taps_per_unit, tap_groups;
+  int group_over_m;  // 1x1 filters: the G accumulators of a unit are G consecutive 128-channel m tiles (tap 0)
   int m_tiles, n_tiles, ksplit;
   int tiles_w, tiles_h, tiles_n;
   int Wb, Hb, Nb;
@@ -334,8 +335,9 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   u /= p.n_tiles;
   const int tg = u % p.tap_groups;
   const int ks = u / p.tap_groups;
-  const int tap0 = tg * G;
-  const int ntap = min(G, p.num_taps - tap0);
+  const int tap0 = p.group_over_m ? 0 : tg * G;
+  const int mt0 = p.group_over_m ? mt * G : mt;  // first 128-channel tile of this unit
+  const int ntap = p.group_over_m ? min(G, (p.cin + 127) / 128 - mt0) : min(G, p.num_taps - tap0);
   const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
   const int per = (total_chunks + p.ksplit - 1) / p.ksplit;
   const int c_begin = ks * per;
@@ -356,10 +358,11 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         for (int b = 0; b < BN / 64; ++b)
           tma_load_4d(&p.dy_map, &full[stage], st + b * kBoxBytes, nt * BN + b * 64, w0, h0, n0);
         for (int g = 0; g < ntap; ++g) {
-          const int tap = tap0 + g;
+          const int tap = p.group_over_m ? 0 : tap0 + g;
+          const int mtile = p.group_over_m ? mt0 + g : mt0;
           const CUtensorMap* xm = &p.x_maps[p.taps.view[tap]];
           for (int b = 0; b < p.a_boxes; ++b)
-            tma_load_4d(xm, &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, mt * 128 + b * 64,
+            tma_load_4d(xm, &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, mtile * 128 + b * 64,
                         w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
         }
         if (++stage == stages) {
@@ -395,11 +398,11 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
     }
   } else if (c_end > c_begin) {
     const int q = warp & 3;
-    const int ci = mt * 128 + q * 32 + lane;
     mbar_wait(tfull, 0);
     tc_fence_after();
     for (int g = 0; g < ntap; ++g) {
-      const int tap = tap0 + g;
+      const int tap = p.group_over_m ? 0 : tap0 + g;
+      const int ci = (p.group_over_m ? mt0 + g : mt0) * 128 + q * 32 + lane;
       float* out = p.dw + static_cast<int64_t>(tap) * p.cin + ci;
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
@@ -592,6 +595,14 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   p.taps_per_unit = num_taps == 9 ? 3 : (num_taps < 4 ? num_taps : 4);  // G * BN <= 512 columns, >= 2 smem stages
   p.tap_groups = (num_taps + p.taps_per_unit - 1) / p.taps_per_unit;
   p.m_tiles = (cin + 127) / 128;
+  if (num_taps == 1 && cin >= 256) {
+    // dY (the wide operand) is loaded once per pixel chunk and multiplied with G input-channel tiles
+    p.group_over_m = 1;
+    p.taps_per_unit = 512 / BN < p.m_tiles ? 512 / BN : p.m_tiles;
+    if (p.taps_per_unit > 4) p.taps_per_unit = 4;  // keep >= 2 pipeline stages in shared memory
+    p.tap_groups = 1;
+    p.m_tiles = (p.m_tiles + p.taps_per_unit - 1) / p.taps_per_unit;
+  }
   p.n_tiles = cout / BN;
   p.a_boxes = cin >= 128 ? 2 : 1;
   p.Wb = bw, p.Hb = bh, p.Nb = bn;

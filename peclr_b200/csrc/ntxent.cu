@@ -50,7 +50,7 @@ struct NtxentArgs {
   int B, world, rank;
   int img_h, img_w, crop, rotate;
   float inv_t;
-  unsigned epoch;
+  unsigned* launch_ctr;    // [1] launches so far (device side, so a captured CUDA graph can be replayed)
   int col_chunk;           // columns per P3 unit (multiple of CB)
   int plain;               // 1: p already holds z (plain NT-Xent, no normalisation / correction / stats)
 };
@@ -96,6 +96,11 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   const int n_glob = n_loc * a.world;
   const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
   unsigned bar_target = 0;
+  // launch number (1-based).  With world > 1 it tags the peer flags and selects one of two z buffers, so a fast
+  // rank's next step never overwrites embeddings a slower rank is still reading.
+  const unsigned epoch = *a.launch_ctr + 1;
+  const size_t zsel = a.world > 1 ? (size_t)(epoch & 1) * (size_t)(2 * a.B * a.world) * D : 0;
+  float* const zbuf = a.z + zsel;
 
   // ---------------------------------------------------------------- P1
   if (blockIdx.x == 0 && threadIdx.x < 17) {
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   for (int i = gwarp; i < n_loc; i += nwarps) {
     const float4 v = reinterpret_cast<const float4*>(a.p + (size_t)i * D)[lane];  // points 2l, 2l+1
     if (a.plain) {
-      reinterpret_cast<float4*>(a.z + (size_t)global_row(i, a.B, a.world, a.rank) * D)[lane] = v;
+      reinterpret_cast<float4*>(zbuf + (size_t)global_row(i, a.B, a.world, a.rank) * D)[lane] = v;
       if (a.g_p) reinterpret_cast<float4*>(a.gz + (size_t)i * D)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
@@ -153,9 +158,10 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
     const float4 zv = make_float4(x0 * inv_r, y0 * inv_r, x1 * inv_r, y1 * inv_r);
     const int gi = global_row(i, a.B, a.world, a.rank);
     if (a.world == 1) {
-      reinterpret_cast<float4*>(a.z + (size_t)gi * D)[lane] = zv;
+      reinterpret_cast<float4*>(zbuf + (size_t)gi * D)[lane] = zv;
     } else {
-      for (int r = 0; r < a.world; ++r) reinterpret_cast<float4*>(a.z_peers[r] + (size_t)gi * D)[lane] = zv;
+      for (int r = 0; r < a.world; ++r)
+        reinterpret_cast<float4*>(a.z_peers[r] + zsel + (size_t)gi * D)[lane] = zv;
     }
     if (lane == 0) reinterpret_cast<float4*>(a.rowbuf)[i] = make_float4(inv_p, inv_r, al, be);
     if (a.g_p) reinterpret_cast<float4*>(a.gz + (size_t)i * D)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -167,13 +173,13 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
     if (blockIdx.x == 0 && threadIdx.x < a.world) {
       __threadfence_system();
       unsigned* remote = a.flag_peers[threadIdx.x] + a.rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(remote), "r"(a.epoch) : "memory");
+      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(remote), "r"(epoch) : "memory");
       const unsigned* mine = a.flag_peers[a.rank] + threadIdx.x;
       unsigned v = 0, spins = 0;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
         if (++spins > (1u << 28)) __trap();
-      } while (v != a.epoch);
+      } while (v < epoch);
     }
     bar_target += gridDim.x;
     grid_barrier(a.barrier, bar_target);
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
       for (int t = threadIdx.x; t < (RB + CB) * (D / 4); t += 256) {
         const int row = t / (D / 4), c4 = t % (D / 4);
         const int g = row < RB ? i0 + row : k0 + (row - RB);
-        const float4 v = g < n_glob ? reinterpret_cast<const float4*>(a.z + (size_t)g * D)[c4]
+        const float4 v = g < n_glob ? reinterpret_cast<const float4*>(zbuf + (size_t)g * D)[c4]
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         float* dst = (row < RB ? sI + row * LDS : sK + (row - RB) * LDS) + c4 * 4;
         *reinterpret_cast<float4*>(dst) = v;
@@ -233,6 +239,8 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   bar_target += gridDim.x;
   grid_barrier(a.barrier, bar_target);
 
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.launch_ctr = epoch;  // every block read it before the barriers
+
   // ---------------------------------------------------------------- P3: g_z for LOCAL rows
   if (a.g_p) {
     const int rbs = (n_loc + RB - 1) / RB;
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         const int row = t / (D / 4), c4 = t % (D / 4);
         const int li = i0 + row;
         const float4 v = li < n_loc ? reinterpret_cast<const float4*>(
-                                          a.z + (size_t)global_row(li, a.B, a.world, a.rank) * D)[c4]
+                                          zbuf + (size_t)global_row(li, a.B, a.world, a.rank) * D)[c4]
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(sI + row * LDS + c4 * 4) = v;
       }
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         for (int t = threadIdx.x; t < CB * (D / 4); t += 256) {
           const int row = t / (D / 4), c4 = t % (D / 4);
           const int g = k0 + row;
-          const float4 v = g < kend ? reinterpret_cast<const float4*>(a.z + (size_t)g * D)[c4]
+          const float4 v = g < kend ? reinterpret_cast<const float4*>(zbuf + (size_t)g * D)[c4]
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(sK + row * LDS + c4 * 4) = v;
         }
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
     }
     const float4 rb = reinterpret_cast<const float4*>(a.rowbuf)[i];
     const float inv_p = rb.x, inv_r = rb.y, al = rb.z, be = rb.w;
-    const float4 zv = reinterpret_cast<const float4*>(a.z + (size_t)gi * D)[lane];
+    const float4 zv = reinterpret_cast<const float4*>(zbuf + (size_t)gi * D)[lane];
     const float4 g = reinterpret_cast<const float4*>(a.gz + (size_t)i * D)[lane];
     // through the second normalisation: g_r = (g_z - z (z . g_z)) / |r|
     const float dot = warp_sum(zv.x * g.x + zv.y * g.y + zv.z * g.z + zv.w * g.w);
@@ -373,15 +381,15 @@ using namespace peclr;
 
 extern "C" long long peclr_ntxent_workspace_bytes(int B, int world) {
   const long long n_loc = 2LL * B, n_glob = n_loc * world;
-  // z [n_glob][128] | rowbuf [n_loc][4] | neg [n_glob] | spos [n_glob] | gz [n_loc][128] | barrier
-  return 4 * (n_glob * D + n_loc * 4 + 2 * n_glob + n_loc * D) + 256;
+  // z [1 or 2][n_glob][128] | rowbuf [n_loc][4] | neg [n_glob] | spos [n_glob] | gz [n_loc][128] | barrier, counter
+  const long long zbufs = world > 1 ? 2 : 1;
+  return 4 * (zbufs * n_glob * D + n_loc * 4 + 2 * n_glob + n_loc * D) + 256;
 }
 
 static int ntxent_launch(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
                          int dim, int img_h, int img_w, int crop, int rotate, float temperature, float* loss,
                          float* stats, float* g_p, void* workspace, long long workspace_bytes, int world, int rank,
-                         float* const* z_peers, unsigned* const* flag_peers, unsigned epoch, int plain,
-                         void* stream) {
+                         float* const* z_peers, unsigned* const* flag_peers, int plain, void* stream) {
   if (dim != D || B < 1 || world < 1 || rank < 0 || rank >= world) return -1001;
   if (workspace_bytes < peclr_ntxent_workspace_bytes(B, world)) return -1001;
   if ((crop && (!jx || !jy)) || (rotate && !angle)) return -1001;
@@ -391,17 +399,17 @@ static int ntxent_launch(const float* p, const double* angle, const long long* j
   float* ws = static_cast<float*>(workspace);
   a.p = p, a.angle = angle, a.jx = jx, a.jy = jy;
   a.z = ws;
-  a.rowbuf = a.z + n_glob * D;
+  a.rowbuf = a.z + (world > 1 ? 2 : 1) * n_glob * D;
   a.neg = a.rowbuf + n_loc * 4;
   a.spos = a.neg + n_glob;
   a.gz = a.spos + n_glob;
   a.barrier = reinterpret_cast<unsigned*>(a.gz + n_loc * D);
+  a.launch_ctr = a.barrier + 8;  // lives in the (zero-initialised) workspace, advanced by the kernel
   a.z_peers = z_peers, a.flag_peers = flag_peers;
   a.loss = loss, a.stats = stats, a.g_p = g_p;
   a.B = B, a.world = world, a.rank = rank;
   a.img_h = img_h, a.img_w = img_w, a.crop = crop, a.rotate = rotate;
   a.inv_t = 1.f / temperature;
-  a.epoch = epoch;
   a.plain = plain;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 148;
@@ -430,15 +438,14 @@ static int ntxent_launch(const float* p, const double* angle, const long long* j
 extern "C" int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
                                   int dim, int img_h, int img_w, int crop, int rotate, float temperature, float* loss,
                                   float* stats, float* g_p, void* workspace, long long workspace_bytes, int world,
-                                  int rank, float* const* z_peers, unsigned* const* flag_peers, unsigned epoch,
-                                  void* stream) {
+                                  int rank, float* const* z_peers, unsigned* const* flag_peers, void* stream) {
   if (!stats) return -1001;
   return ntxent_launch(p, angle, jx, jy, B, dim, img_h, img_w, crop, rotate, temperature, loss, stats, g_p,
-                       workspace, workspace_bytes, world, rank, z_peers, flag_peers, epoch, 0, stream);
+                       workspace, workspace_bytes, world, rank, z_peers, flag_peers, 0, stream);
 }
 
 extern "C" int peclr_ntxent_plain(const float* z, int B, int dim, float temperature, float* loss, float* g_z,
                                   void* workspace, long long workspace_bytes, void* stream) {
   return ntxent_launch(z, nullptr, nullptr, nullptr, B, dim, 1, 1, 0, 0, temperature, loss, nullptr, g_z, workspace,
-                       workspace_bytes, 1, 0, nullptr, nullptr, 0, 1, stream);
+                       workspace_bytes, 1, 0, nullptr, nullptr, 1, stream);
 }

@@ -292,9 +292,8 @@ class StepEngine:
         kw = {}
         if self.world > 1:
             sym = self._symmetric(b)
-            self._epoch += 1
             kw = dict(workspace=sym["ws"], world=self.world, rank=self.rank, z_peers=sym["z_ptrs"],
-                      flag_peers=sym["flag_ptrs"], epoch=self._epoch)
+                      flag_peers=sym["flag_ptrs"])
         else:
             kw = dict(workspace=self.loss_workspace(b))
         return ops.ntxent_fused(p, angle, jx, jy, hw, crop, rotate, temperature, want_grad=want_grad, **kw)

@@ -239,7 +239,7 @@ def ntxent_workspace(batch, world=1, device="cuda"):
 
 
 def ntxent_fused(p, angle, jx, jy, image_hw, crop, rotate, temperature=0.5, want_grad=True, workspace=None,
-                 world=1, rank=0, z_peers=None, flag_peers=None, epoch=0):
+                 world=1, rank=0, z_peers=None, flag_peers=None):
     """Returns loss [1], stats [16], g_p (or None).  p [2B,128] fp32."""
     _need_cuda(p, angle, jx, jy)
     n, d = p.shape
@@ -252,7 +252,7 @@ def ntxent_fused(p, angle, jx, jy, image_hw, crop, rotate, temperature=0.5, want
     g_p = torch.empty_like(p) if want_grad else None
     _lib.call("peclr_ntxent_fused", p, angle if rotate else None, jx if crop else None, jy if crop else None,
               b, d, int(image_hw[0]), int(image_hw[1]), int(crop), int(rotate), float(temperature), loss, stats, g_p,
-              workspace, workspace.numel() * 4, world, rank, z_peers, flag_peers, epoch, _s())
+              workspace, workspace.numel() * 4, world, rank, z_peers, flag_peers, _s())
     return loss, stats, g_p
 
 
