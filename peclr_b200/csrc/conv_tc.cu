@@ -49,11 +49,15 @@ struct GemmParams {
   int reduce_add;
 };
 
-template <int BN, int STAGES>
+// CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
+// 128 pixel rows of A and half of the BN weight rows, so the L2 -> shared-memory traffic per FLOP drops by a
+// third; the leader CTA issues the MMAs, each CTA drains its own 128 TMEM lanes.
+template <int BN, int STAGES, int CTAS>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kStageB = BN * 128;
+  constexpr int kStageB = (BN / CTAS) * 128;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kStageA;
   uint8_t* sD = sB + STAGES * kStageB;
@@ -81,32 +85,36 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 256);
+        mbar_init(&tempty[i], 8 * CTAS);  // one arrival per epilogue warp (of both CTAs: the leader's barrier)
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<2 * BN>(tmem_slot);
+    if constexpr (CTAS == 2) tmem_alloc_2sm<2 * BN>(tmem_slot);
+    else tmem_alloc<2 * BN>(tmem_slot);
   }
   if (want_stats && warp >= 2) {
     for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 256) sStat[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // work items: (pair of) m tiles x n tile; CTA `cta_rank` of a pair owns m tile 2 * pair + cta_rank
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;
+  const int first_tile = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
   const int num_kb = p.num_taps * p.c_chunks;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         const int nt = t % p.n_tiles;
-        const int mt = t / p.n_tiles;
+        const int mt = (t / p.n_tiles) * CTAS + cta_rank;  // may be one past the end: all-OOB boxes (zero fill)
         const int w0 = (mt % p.tiles_w) * p.Wb;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
@@ -117,9 +125,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           const int kbase = p.taps.koff[tap];
           for (int c = 0; c < p.c_chunks; ++c) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], kStageA + kStageB);
-            tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
-            tma_load_2d(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64, nt * BN);
+            if constexpr (CTAS == 2) {
+              // both CTAs' bytes are counted on the leader's barrier
+              if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * (kStageA + kStageB));
+              tma_load_4d_2sm(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
+              tma_load_2d_2sm(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64,
+                              nt * BN + cta_rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full[stage], kStageA + kStageB);
+              tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
+              tma_load_2d(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64, nt * BN);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -129,12 +145,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    if (cta_rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128 * CTAS, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], aphase ^ 1);
@@ -147,15 +163,18 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * kStageB), 0, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the swizzle atom
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (CTAS == 2) umma_commit_2sm(&empty[stage]);
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (CTAS == 2) umma_commit_2sm(&tfull[acc]);
+        else umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -166,11 +185,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int et = threadIdx.x - 64;  // 0..255
     const uint32_t sD32 = smem_u32(sD), sStat32 = smem_u32(sStat);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = t % p.n_tiles;
-      const int mt = t / p.n_tiles;
+      const int mt = (t / p.n_tiles) * CTAS + cta_rank;
       const int w0 = (mt % p.tiles_w) * p.Wb;
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
@@ -197,7 +216,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may reuse it
+      __syncwarp();
+      if (lane == 0) {  // accumulator drained: the (leader's) MMA warp may reuse it
+        if constexpr (CTAS == 2) mbar_arrive_cluster(&tempty[acc], 0);
+        else mbar_arrive(&tempty[acc]);
+      }
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (et == 0) {
@@ -267,9 +290,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (CTAS == 2) tmem_dealloc_2sm<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -513,18 +538,41 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS>
 static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)STAGES * (kStageA + BN * 128) + (size_t)(BN / 64) * kStageA + 256 +
+  const size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) + (size_t)(BN / 64) * kStageA + 256 +
                       (stats ? 2 * (size_t)p.cout * 4 : 0);
-  auto kern = conv_gemm_kernel<BN, STAGES>;
+  auto kern = conv_gemm_kernel<BN, STAGES, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, 320, smem, stream>>>(p);
-  e = cudaGetLastError();
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total = ((m_tiles + CTAS - 1) / CTAS) * p.n_tiles;  // (pairs of) tiles
+  const int slots = sm_count() / CTAS;
+  const int grid = CTAS * (total < slots ? total : slots);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, p);
   return e == cudaSuccess ? 0 : -(int)e;
+}
+
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_CONV_CTA2");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
 }
 
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
@@ -541,7 +589,8 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   for (int i = 0; i < kMaxViews; ++i)
     if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
   const int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
-  if ((rc = encode_matrix(&p.b_map, w, ktot, nout, BN))) return rc;
+  const bool pairs = use_cta_pairs() && d_view.w * d_view.h * d_view.n > 128;  // at least two m tiles
+  if ((rc = encode_matrix(&p.b_map, w, ktot, nout, pairs ? BN / 2 : BN))) return rc;
   if ((rc = encode_view(&p.d_map, d_view, bw, bh, bn))) return rc;
   p.taps = taps;
   p.num_taps = num_taps;
@@ -559,9 +608,14 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.stat_sumsq = stat_sumsq;
   p.reduce_add = reduce_add;
   const bool stats = stat_sum != nullptr;
-  if (BN == 256) return launch_gemm_t<256, 3>(p, stats, stream);
-  if (BN == 128) return launch_gemm_t<128, 4>(p, stats, stream);
-  return launch_gemm_t<64, 6>(p, stats, stream);
+  if (pairs) {
+    if (BN == 256) return launch_gemm_t<256, 4, 2>(p, stats, stream);
+    if (BN == 128) return launch_gemm_t<128, 6, 2>(p, stats, stream);
+    return launch_gemm_t<64, 8, 2>(p, stats, stream);
+  }
+  if (BN == 256) return launch_gemm_t<256, 3, 1>(p, stats, stream);
+  if (BN == 128) return launch_gemm_t<128, 4, 1>(p, stats, stream);
+  return launch_gemm_t<64, 6, 1>(p, stats, stream);
 }
 
 template <int BN>
