@@ -18,21 +18,49 @@ SHAPES = [  # Cin, Hin, Cout, k, s, count50, count152
 ]
 
 
-def timeit(fn, reps=5):
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    fn()
+_FLUSH = None
+
+
+def _graph_time(body, reps=5):
+    """Milliseconds of one replay of a CUDA graph holding `reps` x body() (no host launch latency inside)."""
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            body()
+    g.replay()
     torch.cuda.synchronize()
     ts = []
-    for _ in range(reps):
-        flush.zero_()  # evict L2
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    ts.sort()
-    return ts[len(ts) // 2]
+    return min(ts)
+
+
+def timeit(fn, reps=5):
+    """Per-call device time with the L2 evicted before every call: (flush + fn) x reps minus flush x reps, both
+    replayed from CUDA graphs so that host-side launch latency does not enter."""
+    global _FLUSH
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    flush = _FLUSH
+
+    def both():
+        flush.zero_()
+        fn()
+
+    t_both = _graph_time(both, reps)
+    t_flush = _graph_time(lambda: flush.zero_(), reps)
+    return max(t_both - t_flush, 1e-6) / reps
 
 
 def main():
