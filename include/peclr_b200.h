@@ -53,14 +53,17 @@ int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int
 
 /* out = [relu]( bn(y) + residual ), bn from the conv epilogue's sums over M rows.  residual is NULL, a
  * finished activation (rsum == NULL) or a raw conv output with its own BatchNorm (downsample branch).
- * Saves mean / invstd for backward and updates running stats (momentum, unbiased var) as PyTorch does. */
+ * Saves mean / invstd for backward and updates running stats (momentum, unbiased var) as PyTorch does.
+ * mask_out (optional, uint8 [M][C/8]) receives the ReLU mask as bits for peclr_bn_bwd_* mask_mode 3. */
 int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
                    const void* res, const float* rsum, const float* rsumsq, const float* rgamma, const float* rbeta,
-                   void* out, float* mean_out, float* invstd_out, float* running_mean, float* running_var,
+                   void* out, void* mask_out, float* mean_out, float* invstd_out, float* running_mean,
+                   float* running_var,
                    float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
                    float eps, float momentum, int relu, void* stream);
 /* scratch[0:C] = sum g, scratch[C:2C] = sum g*xhat with g = dout * relu'; the ReLU mask is (mask_mode)
- * 0: none (dout already masked), 1: the stored activation `mask` > 0, 2: recomputed from y, gamma, beta. */
+ * 0: none (dout already masked), 1: the stored activation `mask` > 0, 2: recomputed from y, gamma, beta,
+ * 3: `mask` is the bit mask written by peclr_bn_apply. */
 int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, int mask_mode, float* scratch, long long M, int C,
                         void* stream);

@@ -22,7 +22,7 @@ SIGNATURES = {
     "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P],
     "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
     "peclr_stem_wgrad": [P, P, P, I, I, I, P],
-    "peclr_bn_apply": [P] * 19 + [L, I, F, F, I, P],
+    "peclr_bn_apply": [P] * 20 + [L, I, F, F, I, P],
     "peclr_bn_bwd_reduce": [P, P, P, P, P, P, P, I, P, L, I, P],
     "peclr_bn_bwd_apply": [P, P, P, P, P, P, P, I, P, P, P, P, P, L, I, P],
     "peclr_stem_bn_relu_pool": [P] * 11 + [I, I, I, F, F, P],

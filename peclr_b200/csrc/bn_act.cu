@@ -62,6 +62,7 @@ struct BnApplyArgs {
   const __nv_bfloat16* res;                     // optional second operand of the residual add
   const float *rsum, *rsumsq, *rgamma, *rbeta;  // if non-null, res is a raw conv output with its own BN
   __nv_bfloat16* out;
+  uint8_t* mask_out;  // optional [M][C/8]: bit i of byte (row, channel group) = out[8g + i] > 0
   float *mean_out, *invstd_out, *running_mean, *running_var;
   float *rmean_out, *rinvstd_out, *rrunning_mean, *rrunning_var;
   long long M;
@@ -151,6 +152,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       st8(a.out + rr * a.C + c0, pack8(v));
+      if (a.mask_out) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+        a.mask_out[rr * tpr + cg] = (uint8_t)bits;
+      }
     }
   }
 }
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 // g = dout * relu'(.) where the ReLU mask comes from (mask_mode)
 //   0: nothing (dout is already masked)        1: a stored activation tensor (mask > 0)
 //   2: recomputed from y: fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0  (no extra HBM read)
+//   3: bit mask written by bn_apply (1 byte per 8 channels instead of re-reading the 16-byte activation)
 struct BnBwdArgs {
   const __nv_bfloat16 *dout, *mask, *y;
   const float *mean, *invstd, *gamma, *beta;
@@ -201,6 +209,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
   const long long stride = (long long)gridDim.x * rows_per_block;
   for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M; r += kRows * stride) {
     bf16x8 gv[kRows], yv[kRows], mv[kRows];
+    uint32_t mb[kRows];
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
       const long long rr = r + j * stride;
@@ -208,6 +217,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
         gv[j] = ld8(a.dout + rr * a.C + c0);
         yv[j] = ld8(a.y + rr * a.C + c0);
         if (a.mask_mode == 1) mv[j] = ld8(a.mask + rr * a.C + c0);
+        if (a.mask_mode == 3) mb[j] = reinterpret_cast<const uint8_t*>(a.mask)[rr * tpr + cg];
       }
     }
 #pragma unroll
@@ -222,6 +232,9 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
         unpack8(mv[j], m);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = m[i] > 0.f ? g[i] : 0.f;
+      } else if (a.mask_mode == 3) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = (mb[j] >> i) & 1u ? g[i] : 0.f;
       } else if (a.mask_mode == 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = fmaf(yf[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
@@ -512,13 +525,14 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma,
                               const float* beta, const void* res, const float* rsum, const float* rsumsq,
-                              const float* rgamma, const float* rbeta, void* out, float* mean_out, float* invstd_out,
+                              const float* rgamma, const float* rbeta, void* out, void* mask_out, float* mean_out,
+                              float* invstd_out,
                               float* running_mean, float* running_var, float* rmean_out, float* rinvstd_out,
                               float* rrunning_mean, float* rrunning_var, long long M, int C, float eps, float momentum,
                               int relu, void* stream) {
   if (bad_channels(C)) return -1001;
   BnApplyArgs a{(const bf16*)y, sum,      sumsq,      gamma,        beta,         (const bf16*)res, rsum,
-                rsumsq,         rgamma,   rbeta,      (bf16*)out,   mean_out,     invstd_out,       running_mean,
+                rsumsq,         rgamma,   rbeta,      (bf16*)out,   (uint8_t*)mask_out, mean_out,     invstd_out,       running_mean,
                 running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
                 eps,            momentum, relu};
   const int rows_per_block = 256 / (C / 8);
@@ -529,7 +543,7 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
 extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, int mask_mode,
                                    float* scratch, long long M, int C, void* stream) {
-  if (bad_channels(C) || mask_mode < 0 || mask_mode > 2 || (mask_mode == 1 && !mask)) return -1001;
+  if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)C * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
@@ -543,7 +557,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
                                   const float* invstd, const float* gamma, const float* beta, int mask_mode,
                                   const float* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
                                   long long M, int C, void* stream) {
-  if (bad_channels(C) || mask_mode < 0 || mask_mode > 2 || (mask_mode == 1 && !mask)) return -1001;
+  if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
               (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);

@@ -304,6 +304,7 @@ struct WgradParams {
   CUtensorMap dy_map;
   TapTable taps;
   int num_taps, taps_per_unit, tap_groups;
+  int pair_taps;     // Cin == 64: the two 64-channel halves of the 128-row operand hold two different filter taps
   int group_over_m;  // 1x1 filters: the G accumulators of a unit are G consecutive 128-channel m tiles (tap 0)
   int m_tiles, n_tiles, ksplit;
   int tiles_w, tiles_h, tiles_n;
@@ -362,7 +363,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   const int ks = u / p.tap_groups;
   const int tap0 = p.group_over_m ? 0 : tg * G;
   const int mt0 = p.group_over_m ? mt * G : mt;  // first 128-channel tile of this unit
-  const int ntap = p.group_over_m ? min(G, (p.cin + 127) / 128 - mt0) : min(G, p.num_taps - tap0);
+  const int slots = p.pair_taps ? (p.num_taps + 1) / 2 : p.num_taps;  // accumulators needed for all taps
+  const int ntap = p.group_over_m ? min(G, (p.cin + 127) / 128 - mt0) : min(G, slots - tap0);
   const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
   const int per = (total_chunks + p.ksplit - 1) / p.ksplit;
   const int c_begin = ks * per;
@@ -378,11 +380,22 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         const int n0 = (c / (p.tiles_w * p.tiles_h)) * p.Nb;
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], kBBytes + ntap * p.a_boxes * kBoxBytes);
+        int a_box_count = ntap * p.a_boxes;
+        if (p.pair_taps && 2 * (tap0 + ntap) > p.num_taps) --a_box_count;  // odd tap count: last half stays empty
+        mbar_expect_tx(&full[stage], kBBytes + a_box_count * kBoxBytes);
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
           tma_load_4d(&p.dy_map, &full[stage], st + b * kBoxBytes, nt * BN + b * 64, w0, h0, n0);
         for (int g = 0; g < ntap; ++g) {
+          if (p.pair_taps) {
+            for (int b = 0; b < 2; ++b) {
+              const int tap = 2 * (tap0 + g) + b;
+              if (tap >= p.num_taps) break;
+              tma_load_4d(&p.x_maps[p.taps.view[tap]], &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, 0,
+                          w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
+            }
+            continue;
+          }
           const int tap = p.group_over_m ? 0 : tap0 + g;
           const int mtile = p.group_over_m ? mt0 + g : mt0;
           const CUtensorMap* xm = &p.x_maps[p.taps.view[tap]];
@@ -426,8 +439,13 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
     mbar_wait(tfull, 0);
     tc_fence_after();
     for (int g = 0; g < ntap; ++g) {
-      const int tap = p.group_over_m ? 0 : tap0 + g;
-      const int ci = (p.group_over_m ? mt0 + g : mt0) * 128 + q * 32 + lane;
+      int tap = p.group_over_m ? 0 : tap0 + g;
+      int ci = (p.group_over_m ? mt0 + g : mt0) * 128 + q * 32 + lane;
+      if (p.pair_taps) {  // rows 0..63 belong to tap 2s, rows 64..127 to tap 2s + 1
+        tap = 2 * (tap0 + g) + (q >> 1);
+        ci = (q & 1) * 32 + lane;
+        if (tap >= p.num_taps) ci = p.cin;  // nothing to write
+      }
       float* out = p.dw + static_cast<int64_t>(tap) * p.cin + ci;
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
@@ -649,6 +667,13 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   p.taps_per_unit = num_taps == 9 ? 3 : (num_taps < 4 ? num_taps : 4);  // G * BN <= 512 columns, >= 2 smem stages
   p.tap_groups = (num_taps + p.taps_per_unit - 1) / p.taps_per_unit;
   p.m_tiles = (cin + 127) / 128;
+  if (num_taps > 1 && cin == 64) {
+    p.pair_taps = 1;
+    p.a_boxes = 2;
+    const int slots = (num_taps + 1) / 2;
+    p.taps_per_unit = slots == 5 ? 3 : 2;
+    p.tap_groups = (slots + p.taps_per_unit - 1) / p.taps_per_unit;
+  }
   if (num_taps == 1 && cin >= 256) {
     // dY (the wide operand) is loaded once per pixel chunk and multiplied with G input-channel tiles
     p.group_over_m = 1;
@@ -658,7 +683,7 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
     p.m_tiles = (p.m_tiles + p.taps_per_unit - 1) / p.taps_per_unit;
   }
   p.n_tiles = cout / BN;
-  p.a_boxes = cin >= 128 ? 2 : 1;
+  p.a_boxes = (cin >= 128 || p.pair_taps) ? 2 : 1;
   p.Wb = bw, p.Hb = bh, p.Nb = bn;
   p.tiles_w = (int)((dy_view.w + bw - 1) / bw);
   p.tiles_h = (int)((dy_view.h + bh - 1) / bh);

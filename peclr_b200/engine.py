@@ -232,6 +232,8 @@ class StepEngine:
                     rec["convs"].append((conv, bn, x, y, act, sv))
                     x = act
                 else:
+                    # ReLU mask of the block output as bits (1 byte per 8 channels) for the backward pass
+                    mbits = torch.empty((m, conv.cout // 8), dtype=torch.uint8, device=dev) if training else None
                     if blk.downsample is not None:
                         dconv, dbn = blk.downsample[0], blk.downsample[1]
                         dst, dsv = slab(dconv.cout)
@@ -242,12 +244,13 @@ class StepEngine:
                             relu=True, res=yd,
                             res_bn=(self._bn_stats_for(dbn, m, training, dst), self._p(dbn, "weight"),
                                     self._p(dbn, "bias"), run(dbn)),
-                            running=run(bn), eps=bn.eps, momentum=bn.momentum, saved=sv, rsaved=dsv)
+                            running=run(bn), eps=bn.eps, momentum=bn.momentum, saved=sv, rsaved=dsv, mask_out=mbits)
                         rec["down"] = (dconv, dbn, yd, dsv)
                     else:
                         out, _ = ops.bn_apply(y, self._bn_stats_for(bn, m, training, st), self._p(bn, "weight"),
                                               self._p(bn, "bias"), relu=True, res=rec["a_in"], running=run(bn),
-                                              eps=bn.eps, momentum=bn.momentum, saved=sv)
+                                              eps=bn.eps, momentum=bn.momentum, saved=sv, mask_out=mbits)
+                    rec["mask"] = mbits
                     rec["convs"].append((conv, bn, x, y, out, sv))
                     a = out
             hh, ww = a.shape[1], a.shape[2]
@@ -351,7 +354,7 @@ class StepEngine:
             convs = rec["convs"]
             # last conv of the block: BN backward with the block-output ReLU mask; g feeds the shortcut
             conv, bn, x, y, out, sv = convs[-1]
-            dy, g = ops.bn_backward(da, out, y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
+            dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
                                     self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
             da = None
             ops.conv2d_wgrad(x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"))

@@ -97,7 +97,7 @@ def stem_wgrad(xpad, dy, h, w, dwpack=None):
 
 # ------------------------------------------------------------------ batch norm & friends
 def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=None, eps=1e-5, momentum=0.1, out=None,
-             saved=None, rsaved=None):
+             saved=None, rsaved=None, mask_out=None):
     """out = [relu](bn(y) + res).  res_bn = (stats, gamma, beta, running or None) if res is a raw conv output.
     Returns out, (mean, invstd)[, (rmean, rinvstd)]."""
     c = y.shape[-1]
@@ -112,7 +112,7 @@ def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=No
     _lib.call(
         "peclr_bn_apply", y, stats[0], stats[1], gamma, beta, res,
         rstats[0] if rstats is not None else None, rstats[1] if rstats is not None else None, rgamma, rbeta,
-        out, saved[0], saved[1],
+        out, mask_out, saved[0], saved[1],
         running[0] if running is not None else None, running[1] if running is not None else None,
         rsaved[0] if rsaved is not None else None, rsaved[1] if rsaved is not None else None,
         rrunning[0] if rrunning is not None else None, rrunning[1] if rrunning is not None else None,
@@ -126,7 +126,8 @@ def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratc
     `beta` is given, else none (dout already masked).  dgamma/dbeta are accumulated in place.  Returns dy[, g]."""
     c = y.shape[-1]
     m = y.numel() // c
-    mode = 1 if mask is not None else (2 if beta is not None else 0)
+    # mask: bf16 activation (mode 1) or the uint8 bit mask bn_apply wrote (mode 3)
+    mode = (3 if mask.dtype == torch.uint8 else 1) if mask is not None else (2 if beta is not None else 0)
     if scratch is None:
         scratch = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
     dy = dy if dy is not None else torch.empty_like(y)

@@ -169,6 +169,13 @@ def test_bn_apply_and_backward(ops, c, m):
     assert rel_l2(dy.float().view(m, c), yt.grad) < 1e-2
     assert rel_l2(dgamma, gt.grad) < 2e-3 and rel_l2(dbeta, bt.grad) < 2e-3
     assert torch.equal(gout.float().view(m, c), dout.float() * mask)
+    # the same through the bit mask bn_apply can emit (1 byte per 8 channels)
+    mbits = torch.empty(m, c // 8, dtype=torch.uint8, device="cuda")
+    out2, _ = ops.bn_apply(y.view(m, 1, 1, c), stats, gamma, beta, relu=True, res=res.view(m, 1, 1, c), mask_out=mbits)
+    dg3, db3 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dy3, gout3 = ops.bn_backward(dout.view(m, 1, 1, c), mbits, y.view(m, 1, 1, c), saved, gamma, dg3, db3, want_g=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out) and torch.equal(dy3, dy) and torch.equal(gout3, gout)
     # mask recomputed from y (no residual): compare against torch's relu(bn(y)) backward
     yt2 = yf.clone().requires_grad_()
     torch.relu(F.batch_norm(yt2, None, None, gamma, beta, training=True, eps=1e-5)).backward(dout.float())
