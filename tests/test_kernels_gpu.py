@@ -175,7 +175,8 @@ def test_bn_apply_and_backward(ops, c, m):
     dg3, db3 = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
     dy3, gout3 = ops.bn_backward(dout.view(m, 1, 1, c), mbits, y.view(m, 1, 1, c), saved, gamma, dg3, db3, want_g=True)
     torch.cuda.synchronize()
-    assert torch.equal(out2, out) and torch.equal(dy3, dy) and torch.equal(gout3, gout)
+    assert torch.equal(out2, out) and torch.equal(gout3, gout)  # identical mask
+    assert rel_l2(dy3.float(), dy.float()) < 1e-3  # (the channel sums are accumulated with atomics: order varies)
     # mask recomputed from y (no residual): compare against torch's relu(bn(y)) backward
     yt2 = yf.clone().requires_grad_()
     torch.relu(F.batch_norm(yt2, None, None, gamma, beta, training=True, eps=1e-5)).backward(dout.float())
