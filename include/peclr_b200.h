@@ -61,13 +61,13 @@ int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const fl
                    float* running_var,
                    float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
                    float eps, float momentum, int relu, void* stream);
-/* scratch[0:C] = sum g, scratch[C:2C] = sum g*xhat with g = dout * relu'; the ReLU mask is (mask_mode)
+/* scratch[0:C] = sum g, scratch[C:2C] = sum g*y with g = dout * relu'; the ReLU mask is (mask_mode)
  * 0: none (dout already masked), 1: the stored activation `mask` > 0, 2: recomputed from y, gamma, beta,
  * 3: `mask` is the bit mask written by peclr_bn_apply. */
 int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, int mask_mode, float* scratch, long long M, int C,
                         void* stream);
-/* dy = gamma*invstd*(g - mean g - xhat*mean(g xhat)); optional g_out = g; dgamma/dbeta += scratch */
+/* dy = gamma*invstd*(g - mean g - xhat*mean(g xhat)); optional g_out = g; dbeta += sum g, dgamma += sum g*xhat */
 int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
                        const float* gamma, const float* beta, int mask_mode, const float* scratch, void* dy,
                        void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream);
@@ -77,7 +77,7 @@ int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq,
                             const float* beta, void* out, void* idx_out, float* mean_out, float* invstd_out,
                             float* running_mean, float* running_var, int N, int H, int W, float eps, float momentum,
                             void* stream);
-/* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums into scratch[128] */
+/* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums (sum g, sum g*y) into scratch[128] */
 int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, void* g_out, float* scratch, int N, int H, int W,
                         void* stream);

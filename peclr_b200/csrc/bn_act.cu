@@ -170,36 +170,41 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 struct BnBwdArgs {
   const __nv_bfloat16 *dout, *mask, *y;
   const float *mean, *invstd, *gamma, *beta;
-  float* scratch;          // [2C]: sum g, sum g*xhat
+  float* scratch;          // [2C]: sum g, sum g*y
   __nv_bfloat16 *dy, *g_out;
   float *dgamma, *dbeta;
   long long M;
   int C, mask_mode;
 };
 
-template <bool kApply>
-__global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
+// Pass 1 (kApply = false) accumulates sum g and sum g*y per channel; pass 2 folds everything into three
+// per-channel constants: dy = A*g + B*y + C with A = gamma*invstd, B = -A*invstd*k3, C = -A*(k2 - k3*invstd*mean),
+// k2 = mean(g), k3 = mean(g*xhat) = invstd*(mean(g*y) - mean*mean(g)).  Few live registers -> 3-4 blocks per SM.
+template <bool kApply, int kMask>
+__global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwdArgs a) {
   __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][kApply ? 1 : 9];
   const int tpr = a.C >> 3;
   const int rows_per_block = 256 / tpr;
   const int cg = threadIdx.x % tpr;
   const int roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
-  float mu[8], is[8], scale[8], shift[8], k1[8], k2[8], k3[8], s[8], d[8];
+  float scale[8], shift[8], ka[8], kb[8], kc[8], s[8], d[8];
   const float inv_m = 1.f / (float)a.M;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    mu[i] = a.mean[c0 + i];
-    is[i] = a.invstd[c0 + i];
-    const float gm = a.gamma[c0 + i];
-    scale[i] = gm * is[i];
-    shift[i] = (a.mask_mode == 2 ? a.beta[c0 + i] : 0.f) - mu[i] * scale[i];
+    const float mu = a.mean[c0 + i], is = a.invstd[c0 + i], gm = a.gamma[c0 + i];
+    if (kMask == 2) {
+      scale[i] = gm * is;
+      shift[i] = a.beta[c0 + i] - mu * scale[i];
+    }
     s[i] = d[i] = 0.f;
     if (kApply) {
-      const float sg = a.scratch[c0 + i], sgx = a.scratch[a.C + c0 + i];
-      k1[i] = scale[i];
-      k2[i] = sg * inv_m;
-      k3[i] = sgx * inv_m;
+      const float sg = a.scratch[c0 + i], sgy = a.scratch[a.C + c0 + i];
+      const float sgx = is * (sgy - mu * sg);
+      const float k2 = sg * inv_m, k3 = sgx * inv_m;
+      ka[i] = gm * is;
+      kb[i] = -ka[i] * is * k3;
+      kc[i] = -ka[i] * (k2 - k3 * is * mu);
       if (blockIdx.x == 0 && roff == 0) {
         a.dbeta[c0 + i] += sg;
         a.dgamma[c0 + i] += sgx;
@@ -216,8 +221,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
       if (rr < a.M) {
         gv[j] = ld8(a.dout + rr * a.C + c0);
         yv[j] = ld8(a.y + rr * a.C + c0);
-        if (a.mask_mode == 1) mv[j] = ld8(a.mask + rr * a.C + c0);
-        if (a.mask_mode == 3) mb[j] = reinterpret_cast<const uint8_t*>(a.mask)[rr * tpr + cg];
+        if (kMask == 1) mv[j] = ld8(a.mask + rr * a.C + c0);
+        if (kMask == 3) mb[j] = reinterpret_cast<const uint8_t*>(a.mask)[rr * tpr + cg];
       }
     }
 #pragma unroll
@@ -227,28 +232,28 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
       float g[8], yf[8];
       unpack8(gv[j], g);
       unpack8(yv[j], yf);
-      if (a.mask_mode == 1) {
+      if (kMask == 1) {
         float m[8];
         unpack8(mv[j], m);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = m[i] > 0.f ? g[i] : 0.f;
-      } else if (a.mask_mode == 3) {
+      } else if (kMask == 3) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = (mb[j] >> i) & 1u ? g[i] : 0.f;
-      } else if (a.mask_mode == 2) {
+      } else if (kMask == 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = fmaf(yf[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
       }
       if (kApply) {
         if (a.g_out) st8(a.g_out + rr * a.C + c0, pack8(g));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = k1[i] * (g[i] - k2[i] - (yf[i] - mu[i]) * is[i] * k3[i]);
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(ka[i], g[i], fmaf(kb[i], yf[i], kc[i]));
         st8(a.dy + rr * a.C + c0, pack8(g));
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           s[i] += g[i];
-          d[i] = fmaf(g[i], (yf[i] - mu[i]) * is[i], d[i]);
+          d[i] = fmaf(g[i], yf[i], d[i]);
         }
       }
     }
@@ -268,6 +273,16 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const BnBwdArgs a) {
         red_add_f32(a.scratch + a.C + c0 + i, d[i]);
       }
     }
+  }
+}
+
+template <bool kApply>
+static void launch_bn_bwd(const BnBwdArgs& a, int grid, cudaStream_t st) {
+  switch (a.mask_mode) {
+    case 0: bn_bwd_kernel<kApply, 0><<<grid, 256, 0, st>>>(a); break;
+    case 1: bn_bwd_kernel<kApply, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: bn_bwd_kernel<kApply, 2><<<grid, 256, 0, st>>>(a); break;
+    default: bn_bwd_kernel<kApply, 3><<<grid, 256, 0, st>>>(a); break;
   }
 }
 
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
     for (int i = 0; i < 8; ++i) {
       g[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
       s[i] += g[i];
-      d[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], d[i]);
+      d[i] = fmaf(g[i], yv[i], d[i]);
     }
     st8(g_out + r * C + c0, pack8(g));
   }
@@ -549,7 +564,7 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
               nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_kernel<false><<<grid_for(M, rows_per_block * kRows * 2, 2), 256, 0, (cudaStream_t)stream>>>(a);
+  launch_bn_bwd<false>(a, grid_for(M, rows_per_block * kRows * 2, 4), (cudaStream_t)stream);
   return last_error();
 }
 
@@ -561,7 +576,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
               (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  bn_bwd_kernel<true><<<grid_for(M, rows_per_block * kRows, 2), 256, 0, (cudaStream_t)stream>>>(a);
+  launch_bn_bwd<true>(a, grid_for(M, rows_per_block * kRows, 3), (cudaStream_t)stream);
   return last_error();
 }
 
