@@ -1,0 +1,120 @@
+"""Host-side mirror of the reference interface, no GPU: module / state_dict layout, optimiser groups, schedule,
+flag surface and config merging, synthetic batch schema, and that the step refuses to run without CUDA."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import peclr_oracle as po
+
+
+@pytest.fixture(scope="module")
+def model():
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.hybrid2_model import Hybrid2Model
+
+    cfg = EasyDict(dict(po.default_config(resnet_size="50", batch_size=8, num_samples=8 * 64)))
+    torch.manual_seed(0)
+    return Hybrid2Model(cfg)
+
+
+def test_state_dict_layout_matches_reference_golden(model, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "ckpt_layout.npz"))
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in gold["rn50_keys"]]
+    assert ["x".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in gold["rn50_shapes"]]
+
+
+def test_same_seed_gives_reference_initialisation(model):
+    torch.manual_seed(0)
+    oracle = po.OracleHybrid2Model(po.default_config(resnet_size="50", batch_size=8, num_samples=8 * 64))
+    for (k1, v1), (k2, v2) in zip(oracle.state_dict().items(), model.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+
+
+def test_parameters_are_views_of_one_flat_buffer(model):
+    eng = model.engine
+    assert eng.total == 24623680 and len(eng.segs) == 164  # SURVEY 8(a)-A11 (final_layer excluded: never trained)
+    w = model.encoder.features[0].weight
+    assert w.shape == (64, 3, 7, 7) and w.is_contiguous(memory_format=torch.channels_last)
+    assert w.data_ptr() == eng.flat.data_ptr() and w.grad.data_ptr() == eng.grads.data_ptr()
+    with torch.no_grad():
+        w.view(-1)[0] if w.is_contiguous() else None
+        model.projection_head[3].weight.fill_(0.25)
+    s = eng._seg(model.projection_head[3])
+    assert float(eng.flat[s.begin]) == 0.25
+
+
+def test_optimizer_groups_and_schedule(model):
+    class T:
+        world_size, max_epochs = 1, 100
+
+    model.trainer = T()
+    model.setup("fit")
+    assert model.train_iters_per_epoch == 64
+    (opt,), (sch,) = model.configure_optimizers()
+    # exclude_from_wt_decay quirk of the reference: only names containing "bias"/"bn" are excluded
+    assert [len(g["params"]) for g in opt.param_groups] == [62, 104]
+    assert opt.param_groups[0]["weight_decay"] == 1e-6 and opt.param_groups[1]["weight_decay"] == 0.0
+    assert sch["interval"] == "step" and sch["frequency"] == 1
+    base = 1e-4 * (8 * 1) ** 0.5
+    s = sch["scheduler"]
+    for step in range(700):
+        want = po.warmup_cosine_lr(step, base, 10 * 64, 100 * 64)
+        assert opt.param_groups[0]["lr"] == pytest.approx(want, rel=1e-9, abs=1e-15)
+        s.last_epoch += 1  # advance without an optimizer.step() (no CUDA here)
+        for g, lr in zip(opt.param_groups, s.get_lr()):
+            g["lr"] = lr
+    with pytest.raises(Exception):
+        opt.step()  # the fused optimiser needs the CUDA library path
+
+
+def test_step_refuses_to_run_on_cpu(model):
+    from peclr_b200._lib import PeclrKernelError
+
+    batch = po.synthetic_batch(2, 64, seed=1)
+    with pytest.raises(PeclrKernelError):
+        model.training_step(batch, 0)
+
+
+def test_synthetic_batch_schema_equals_oracle_generator():
+    from peclr_b200.synthetic import SyntheticTwoViewDataset, synthetic_batch
+
+    a, b = synthetic_batch(4, 32, seed=9), po.synthetic_batch(4, 32, seed=9)
+    assert set(a) == set(b) == {"transformed_image1", "transformed_image2", "angle_1", "angle_2", "jitter_x_1",
+                                "jitter_x_2", "jitter_y_1", "jitter_y_2"}
+    for k in a:
+        assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    assert a["angle_1"].dtype == torch.float64 and a["jitter_x_1"].dtype == torch.int64
+    assert float(a["angle_1"].min()) >= -45 and float(a["jitter_x_2"].max()) <= 0 and float(a["jitter_y_1"].min()) >= -14
+    item = SyntheticTwoViewDataset(10, 32, rotate=False)[3]
+    assert "angle_1" not in item and item["transformed_image1"].shape == (3, 32, 32)
+
+
+def test_flag_surface_and_config_merge():
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.experiments_utils import (get_general_args, get_model, update_model_params, update_train_params)
+    from peclr_b200.hybrid2_model import Hybrid2Model
+    from peclr_b200.peclr_training import HYBRID2_CONFIG, TRAINING_CONFIG_PATH, read_json
+
+    args = get_general_args("x", ["--rotate", "--crop", "--color_jitter", "-resnet_size", "152", "-epochs", "100",
+                                  "-batch_size", "64", "-accumulate_grad_batches", "16", "-save_top_k", "1",
+                                  "-save_period", "1", "-num_workers", "8", "-train_ratio", "0.9"])
+    train = update_train_params(args, EasyDict(read_json(TRAINING_CONFIG_PATH)))
+    assert train.batch_size == 64 and train.epochs == 100 and train.accumulate_grad_batches == 16
+    assert train.augmentation_flags.rotate and train.augmentation_flags.crop and not train.augmentation_flags.resize
+    assert train.train_ratio == pytest.approx(0.9) and train.seed == 5
+    mp = update_model_params(EasyDict(read_json(HYBRID2_CONFIG)), args, 1234, train)
+    assert mp.resnet_size == "152" and mp.num_samples == 1234 and mp.batch_size == 64 and mp.num_of_mini_batch == 16
+    assert mp.optimizer == "LARS" and mp.lr == 1e-4  # not given on the command line -> JSON defaults stay
+    assert get_model("hybrid2", False, False) is Hybrid2Model
+    assert get_general_args("x", []).resnet_size == "18"  # reference default (experiments/utils.py:147-152)
+
+
+def test_src_compat_imports():
+    from src.experiments.utils import get_model
+    from src.models.port_model import peclr_to_torchvision
+    from src.models.unsupervised.hybrid2_model import Hybrid2Model
+
+    assert get_model("hybrid2", False, False) is Hybrid2Model and callable(peclr_to_torchvision)
