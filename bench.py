@@ -31,6 +31,15 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read + dram__bytes_write per conv_gemm_kernel launch (average over the launches of one step),
+    from the committed ncu capture (profiles/roofline_r01.json); None if the capture is missing."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -234,7 +243,8 @@ def run_ours(args):
         f_train = F_TRAIN.get((args.model, args.size))
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM fprop+dgrad)",
                 "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(),
+                "peak_source": pk["src"] + " (sustained)",
                 "kernel_ms_per_step": round(times["gemm"], 3),
                 "wgrad_kernel": {"achieved": round(ach_w, 1), "frac": round(ach_w / pk["tf_sustained"], 4),
                                  "kernel_ms_per_step": round(times["wgrad"], 3)},

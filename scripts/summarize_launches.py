@@ -6,6 +6,7 @@ import sys
 
 
 def main(path):
+    path = str(path)
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     per = collections.defaultdict(lambda: collections.defaultdict(float))
@@ -28,6 +29,16 @@ def main(path):
         gb = v["bytes"] / 1e9
         print("%-34s %5d %9.3f %5.1f%% %9.2f %8.0f" % (k[:34], len(ids[k]), v["ms"], 100 * v["ms"] / tot, gb,
                                                       gb / (v["ms"] / 1e3) if v["ms"] else 0))
+
+
+    if len(sys.argv) > 2:  # also write the per-launch DRAM traffic of the dominant kernel class for bench.py
+        import json
+
+        n = sum(len(ids[k]) for k in per if k.startswith("conv_gemm_kernel"))
+        b = sum(v["bytes"] for k, v in per.items() if k.startswith("conv_gemm_kernel"))
+        ms = sum(v["ms"] for k, v in per.items() if k.startswith("conv_gemm_kernel"))
+        json.dump({"kernel": "conv_gemm_kernel", "launches": n, "dram_bytes_per_launch": b / max(n, 1),
+                   "share_of_step_time": ms / tot, "source": path}, open(sys.argv[2], "w"), indent=1)
 
 
 if __name__ == "__main__":
