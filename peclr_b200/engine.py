@@ -12,6 +12,7 @@ operand) and the packed stem weights.  Activations are NHWC bf16; per layer the 
 post-BN activation a are kept for the backward pass (RN50 @ 224^2, 256 images: ~11 GB of 180 GB).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -41,6 +42,8 @@ class StepEngine:
         self._sym = None  # symmetric-memory handles for the fused embedding all-gather
         self._epoch = 0
         self._ws = {}
+        self.overlap_wgrad = os.environ.get("PECLR_OVERLAP_WGRAD", "1") != "0"
+        self._side = None
 
     # ------------------------------------------------------------------ parameter arena
     def _trainable(self):
@@ -342,6 +345,24 @@ class StepEngine:
         n = ctx["n"]
         da = ops.avgpool_bwd(d_enc, ctx["final_shape"])
         scratch = torch.empty((4096,), dtype=torch.float32, device=dev)
+        # Weight gradients are off the critical path (they only feed the optimiser): they go to a side stream so
+        # the tensor-core-bound wgrad kernels overlap with the HBM-bound BatchNorm / dgrad chain.  Their inputs
+        # are kept alive until the streams join (no allocator reuse while the side stream may still read them).
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        side, keep = self._side, []
+        overlap = self.overlap_wgrad
+
+        def wgrad(fn, *alive):
+            if not overlap:
+                return fn()
+            keep.extend(alive)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
         stage_of = {}
         f = self.encoder.features
         for si, layer in enumerate((f[4], f[5], f[6], f[7])):
@@ -357,7 +378,8 @@ class StepEngine:
             dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
                                     self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
             da = None
-            ops.conv2d_wgrad(x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"))
+            wgrad(lambda x=x, dy=dy, conv=conv: ops.conv2d_wgrad(x, dy, conv.k, conv.stride,
+                                                                  dw=self._g(conv, "weight")), x, dy)
             cur_hw = (x.shape[1], x.shape[2])
             for i in range(len(convs) - 1, 0, -1):
                 conv, bn, x, y, act, sv = convs[i]
@@ -366,13 +388,15 @@ class StepEngine:
                 # inner BN + ReLU: the mask is recomputed from y (no read of the stored activation)
                 dy = ops.bn_backward(dx, None, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
                                      self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"))
-                ops.conv2d_wgrad(px, dy, pconv.k, pconv.stride, dw=self._g(pconv, "weight"))
+                wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(px, dy, pconv.k, pconv.stride,
+                                                                         dw=self._g(pconv, "weight")), px, dy)
             conv1 = convs[0][0]
             if "down" in rec:
                 dconv, dbn, yd, dsv = rec["down"]
                 dyd = ops.bn_backward(g, None, yd, dsv, self._p(dbn, "weight"), self._g(dbn, "weight"),
                                       self._g(dbn, "bias"), scratch=scratch, dy=g)
-                ops.conv2d_wgrad(a_in, dyd, 1, dconv.stride, dw=self._g(dconv, "weight"))
+                wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: ops.conv2d_wgrad(a_in, dyd, 1, dconv.stride,
+                                                                               dw=self._g(dconv, "weight")), a_in, dyd)
                 da = ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride)
                 ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride, out=da, accumulate=True)
             else:
@@ -389,6 +413,9 @@ class StepEngine:
                                         self._g(bn0, "weight"), self._g(bn0, "bias"), scratch=scratch)
         dwp = ops.stem_wgrad(xpad, dy0, h, w)
         _lib.call("peclr_stem_unpack_grad", dwp, self._g(self.stem_conv, "weight"), ops._s())
+        if overlap:
+            main.wait_stream(side)  # join: all weight gradients are complete when backward returns
+        keep.clear()
         if after_stage is not None:
             after_stage(-1)
 
