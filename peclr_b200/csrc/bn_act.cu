@@ -14,7 +14,7 @@
 
 namespace peclr {
 
-constexpr int kRows = 4;  // rows (16-byte loads) in flight per thread
+constexpr int kRowsDefault = 4;  // rows (16-byte loads) in flight per thread (PECLR_ELT_ROWS overrides: 2, 4, 8)
 
 struct alignas(16) bf16x8 {
   uint32_t v[4];
@@ -87,6 +87,7 @@ __device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const flo
   }
 }
 
+template <int kRows>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int tpr = a.C >> 3;  // threads per row
   const int rows_per_block = 256 / tpr;
@@ -180,7 +181,7 @@ struct BnBwdArgs {
 // Pass 1 (kApply = false) accumulates sum g and sum g*y per channel; pass 2 folds everything into three
 // per-channel constants: dy = A*g + B*y + C with A = gamma*invstd, B = -A*invstd*k3, C = -A*(k2 - k3*invstd*mean),
 // k2 = mean(g), k3 = mean(g*xhat) = invstd*(mean(g*y) - mean*mean(g)).  Few live registers -> 3-4 blocks per SM.
-template <bool kApply, int kMask>
+template <bool kApply, int kMask, int kRows>
 __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwdArgs a) {
   __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][kApply ? 1 : 9];
   const int tpr = a.C >> 3;
@@ -276,14 +277,31 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
   }
 }
 
+static int elt_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_ELT_ROWS");
+    v = e ? atoi(e) : kRowsDefault;
+    if (v != 2 && v != 4 && v != 8) v = kRowsDefault;
+  }
+  return v;
+}
+
+template <bool kApply, int kRows>
+static void launch_bn_bwd_r(const BnBwdArgs& a, int grid, cudaStream_t st) {
+  switch (a.mask_mode) {
+    case 0: bn_bwd_kernel<kApply, 0, kRows><<<grid, 256, 0, st>>>(a); break;
+    case 1: bn_bwd_kernel<kApply, 1, kRows><<<grid, 256, 0, st>>>(a); break;
+    case 2: bn_bwd_kernel<kApply, 2, kRows><<<grid, 256, 0, st>>>(a); break;
+    default: bn_bwd_kernel<kApply, 3, kRows><<<grid, 256, 0, st>>>(a); break;
+  }
+}
 template <bool kApply>
 static void launch_bn_bwd(const BnBwdArgs& a, int grid, cudaStream_t st) {
-  switch (a.mask_mode) {
-    case 0: bn_bwd_kernel<kApply, 0><<<grid, 256, 0, st>>>(a); break;
-    case 1: bn_bwd_kernel<kApply, 1><<<grid, 256, 0, st>>>(a); break;
-    case 2: bn_bwd_kernel<kApply, 2><<<grid, 256, 0, st>>>(a); break;
-    default: bn_bwd_kernel<kApply, 3><<<grid, 256, 0, st>>>(a); break;
-  }
+  const int r = elt_rows();
+  if (r == 2) launch_bn_bwd_r<kApply, 2>(a, grid, st);
+  else if (r == 8) launch_bn_bwd_r<kApply, 8>(a, grid, st);
+  else launch_bn_bwd_r<kApply, 4>(a, grid, st);
 }
 
 // ---- stem: a = maxpool3x3/s2/p1(relu(bn(y))), y [N][H][W][64] -> a [N][H/2][W/2][64] ----------------
@@ -514,7 +532,7 @@ static int num_sms() {
 }
 // grid for a row-walking kernel: enough blocks for `rows` at `rows_per_block * unroll` rows per block
 // iteration, capped at `waves` resident blocks per SM.
-static int grid_for(long long work_items, int per_block, int waves = 8) {
+static int grid_for(long long work_items, int per_block, int waves = 2) {
   static int env_waves = -1;  // tuning knob: PECLR_ELT_WAVES overrides the resident-blocks-per-SM cap
   if (env_waves < 0) {
     const char* e = getenv("PECLR_ELT_WAVES");
@@ -551,7 +569,11 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
                 running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
                 eps,            momentum, relu};
   const int rows_per_block = 256 / (C / 8);
-  bn_apply_kernel<<<grid_for(M, rows_per_block * kRows, 4), 256, 0, (cudaStream_t)stream>>>(a);
+  const int kr = elt_rows();
+  const int grid = grid_for(M, rows_per_block * kr);
+  if (kr == 2) bn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else if (kr == 8) bn_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else bn_apply_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
 
@@ -564,7 +586,7 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
               nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  launch_bn_bwd<false>(a, grid_for(M, rows_per_block * kRows * 2, 4), (cudaStream_t)stream);
+  launch_bn_bwd<false>(a, grid_for(M, rows_per_block * elt_rows() * 2), (cudaStream_t)stream);
   return last_error();
 }
 
@@ -576,7 +598,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
               (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
   const int rows_per_block = 256 / (C / 8);
-  launch_bn_bwd<true>(a, grid_for(M, rows_per_block * kRows, 3), (cudaStream_t)stream);
+  launch_bn_bwd<true>(a, grid_for(M, rows_per_block * elt_rows()), (cudaStream_t)stream);
   return last_error();
 }
 
