@@ -56,6 +56,30 @@ __device__ __forceinline__ void bn_coeffs(const float* sum, const float* sumsq, 
   }
 }
 
+// Row schedule of a block: grid-strided (rows interleaved across blocks) or one contiguous range per block.
+struct RowWalk {
+  long long r0, rend, rstep, jstride;
+};
+template <int kRows>
+__device__ __forceinline__ RowWalk row_walk(long long M, int rows_per_block, int roff, int contig) {
+  RowWalk w;
+  if (contig) {
+    const long long unit = (long long)kRows * rows_per_block;
+    const long long per = ((M + gridDim.x - 1) / gridDim.x + unit - 1) / unit * unit;
+    w.r0 = (long long)blockIdx.x * per + roff;
+    w.rend = min(M, ((long long)blockIdx.x + 1) * per);
+    w.rstep = unit;
+    w.jstride = rows_per_block;
+  } else {
+    const long long stride = (long long)gridDim.x * rows_per_block;
+    w.r0 = (long long)blockIdx.x * rows_per_block + roff;
+    w.rend = M;
+    w.rstep = kRows * stride;
+    w.jstride = stride;
+  }
+  return w;
+}
+
 struct BnApplyArgs {
   const __nv_bfloat16* y;
   const float *sum, *sumsq, *gamma, *beta;
@@ -69,6 +93,7 @@ struct BnApplyArgs {
   int C;
   float eps, momentum;
   int relu;
+  int contig;  // 1: each block walks one contiguous row range (DRAM locality) instead of a grid-strided one
 };
 
 __device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const float (&invstd)[8], int c0, long long M,
@@ -123,21 +148,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   if (blockIdx.x == 0 && roff == 0)
     bn_bookkeeping(mean, invstd, c0, a.M, a.eps, a.momentum, a.mean_out, a.invstd_out, a.running_mean, a.running_var);
 
-  const long long stride = (long long)gridDim.x * rows_per_block;
-  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M; r += kRows * stride) {
+  const RowWalk rw = row_walk<kRows>(a.M, rows_per_block, roff, a.contig);
+  for (long long r = rw.r0; r < rw.rend; r += rw.rstep) {
     bf16x8 yv[kRows], rv[kRows];
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
-      const long long rr = r + j * stride;
-      if (rr < a.M) {
+      const long long rr = r + j * rw.jstride;
+      if (rr < rw.rend) {
         yv[j] = ld8(a.y + rr * a.C + c0);
         if (has_res) rv[j] = ld8(a.res + rr * a.C + c0);
       }
     }
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
-      const long long rr = r + j * stride;
-      if (rr >= a.M) break;
+      const long long rr = r + j * rw.jstride;
+      if (rr >= rw.rend) break;
       float v[8];
       unpack8(yv[j], v);
 #pragma unroll
@@ -176,6 +201,7 @@ struct BnBwdArgs {
   float *dgamma, *dbeta;
   long long M;
   int C, mask_mode;
+  int contig;
 };
 
 // Pass 1 (kApply = false) accumulates sum g and sum g*y per channel; pass 2 folds everything into three
@@ -212,14 +238,14 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
       }
     }
   }
-  const long long stride = (long long)gridDim.x * rows_per_block;
-  for (long long r = (long long)blockIdx.x * rows_per_block + roff; r < a.M; r += kRows * stride) {
+  const RowWalk rw = row_walk<kRows>(a.M, rows_per_block, roff, a.contig);
+  for (long long r = rw.r0; r < rw.rend; r += rw.rstep) {
     bf16x8 gv[kRows], yv[kRows], mv[kRows];
     uint32_t mb[kRows];
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
-      const long long rr = r + j * stride;
-      if (rr < a.M) {
+      const long long rr = r + j * rw.jstride;
+      if (rr < rw.rend) {
         gv[j] = ld8(a.dout + rr * a.C + c0);
         yv[j] = ld8(a.y + rr * a.C + c0);
         if (kMask == 1) mv[j] = ld8(a.mask + rr * a.C + c0);
@@ -228,8 +254,8 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
     }
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
-      const long long rr = r + j * stride;
-      if (rr >= a.M) break;
+      const long long rr = r + j * rw.jstride;
+      if (rr >= rw.rend) break;
       float g[8], yf[8];
       unpack8(gv[j], g);
       unpack8(yv[j], yf);
@@ -275,6 +301,15 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
       }
     }
   }
+}
+
+static int elt_contig() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_ELT_CONTIG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 static int elt_rows() {
@@ -567,7 +602,7 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
   BnApplyArgs a{(const bf16*)y, sum,      sumsq,      gamma,        beta,         (const bf16*)res, rsum,
                 rsumsq,         rgamma,   rbeta,      (bf16*)out,   (uint8_t*)mask_out, mean_out,     invstd_out,       running_mean,
                 running_var,    rmean_out, rinvstd_out, rrunning_mean, rrunning_var, M,              C,
-                eps,            momentum, relu};
+                eps,            momentum, relu, elt_contig()};
   const int rows_per_block = 256 / (C / 8);
   const int kr = elt_rows();
   const int grid = grid_for(M, rows_per_block * kr);
@@ -584,7 +619,7 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)C * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
-              nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode};
+              nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode, elt_contig()};
   const int rows_per_block = 256 / (C / 8);
   launch_bn_bwd<false>(a, grid_for(M, rows_per_block * elt_rows() * 2), (cudaStream_t)stream);
   return last_error();
@@ -596,7 +631,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
                                   long long M, int C, void* stream) {
   if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
-              (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode};
+              (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode, elt_contig()};
   const int rows_per_block = 256 / (C / 8);
   launch_bn_bwd<true>(a, grid_for(M, rows_per_block * elt_rows()), (cudaStream_t)stream);
   return last_error();
