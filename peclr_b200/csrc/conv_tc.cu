@@ -690,11 +690,11 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   p.tiles_n = (int)((dy_view.n + bn - 1) / bn);
   const int chunks = p.tiles_w * p.tiles_h * p.tiles_n;
   const int base_units = p.m_tiles * p.n_tiles * p.tap_groups;
-  static int split_waves = -1;  // tuning knob: PECLR_WGRAD_WAVES = target CTAs per SM (default 2)
+  static int split_waves = -1;  // tuning knob: PECLR_WGRAD_WAVES = target CTAs per SM (default 1, measured best)
   if (split_waves < 0) {
     const char* e = getenv("PECLR_WGRAD_WAVES");
-    split_waves = e ? atoi(e) : 2;
-    if (split_waves < 1) split_waves = 2;
+    split_waves = e ? atoi(e) : 1;
+    if (split_waves < 1) split_waves = 1;
   }
   int ksplit = (split_waves * sm_count() + base_units - 1) / base_units;
   const int max_split = (chunks + 7) / 8;  // at least 8 pixel chunks (512 pixels) per unit
