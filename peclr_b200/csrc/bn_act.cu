@@ -14,7 +14,7 @@
 
 namespace peclr {
 
-constexpr int kRowsDefault = 4;  // rows (16-byte loads) in flight per thread (PECLR_ELT_ROWS overrides: 2, 4, 8)
+constexpr int kRowsDefault = 4;  // rows (16-byte loads) in flight per thread (PECLR_ELT_ROWS overrides: 2 or 4)
 
 struct alignas(16) bf16x8 {
   uint32_t v[4];
@@ -317,7 +317,7 @@ static int elt_rows() {
   if (v < 0) {
     const char* e = getenv("PECLR_ELT_ROWS");
     v = e ? atoi(e) : kRowsDefault;
-    if (v != 2 && v != 4 && v != 8) v = kRowsDefault;
+    if (v != 2 && v != 4) v = kRowsDefault;
   }
   return v;
 }
@@ -335,7 +335,6 @@ template <bool kApply>
 static void launch_bn_bwd(const BnBwdArgs& a, int grid, cudaStream_t st) {
   const int r = elt_rows();
   if (r == 2) launch_bn_bwd_r<kApply, 2>(a, grid, st);
-  else if (r == 8) launch_bn_bwd_r<kApply, 8>(a, grid, st);
   else launch_bn_bwd_r<kApply, 4>(a, grid, st);
 }
 
@@ -345,10 +344,11 @@ static void launch_bn_bwd(const BnBwdArgs& a, int grid, cudaStream_t st) {
 __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y,
                                                                 const float* sum, const float* sumsq,
                                                                 const float* gamma, const float* beta,
-                                                                __nv_bfloat16* out, uint8_t* idx_out,
-                                                                float* mean_out, float* invstd_out,
-                                                                float* running_mean, float* running_var, int N,
-                                                                int H, int W, float eps, float momentum) {
+                                                                __nv_bfloat16* __restrict__ out,
+                                                                uint8_t* __restrict__ idx_out, float* mean_out,
+                                                                float* invstd_out, float* running_mean,
+                                                                float* running_var, int N, int H, int W, float eps,
+                                                                float momentum) {
   const int C = 64, tpr = 8;
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
@@ -363,40 +363,43 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
   if (blockIdx.x == 0 && roff == 0)
     bn_bookkeeping(mean, invstd, c0, M, eps, momentum, mean_out, invstd_out, running_mean, running_var);
   const int Ho = H / 2, Wo = W / 2;
-  const long long Mo = (long long)N * Ho * Wo;
-  for (long long r = (long long)blockIdx.x * 32 + roff; r < Mo; r += (long long)gridDim.x * 32) {
-    const int wo = (int)(r % Wo);
-    const int ho = (int)((r / Wo) % Ho);
-    const long long n = r / ((long long)Wo * Ho);
-    bf16x8 win[9];
-    bool ok[9];
+  // one block iteration = one output row (n, ho); 32 pixel lanes x 8 channel groups walk it (no div/mod inside)
+  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
+    const int n = row / Ho, ho = row - n * Ho;
+    const __nv_bfloat16* img = y + (size_t)n * H * W * C + c0;
+#pragma unroll 2
+    for (int wo = roff; wo < Wo; wo += 32) {
+      bf16x8 win[9];
+      bool ok[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const int h = 2 * ho + k / 3 - 1, w = 2 * wo + k % 3 - 1;
-      ok[k] = h >= 0 && h < H && w >= 0 && w < W;
-      if (ok[k]) win[k] = ld8_cached(y + ((n * H + h) * W + w) * C + c0);
-    }
-    float best[8];
-    uint32_t bidx[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) best[i] = -1.f, bidx[i] = 0;  // relu output >= 0 > -1
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (!ok[k]) continue;
-      float v[8];
-      unpack8(win[k], v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float act = fmaxf(fmaf(v[i], scale[i], shift[i]), 0.f);
-        if (act > best[i]) best[i] = act, bidx[i] = k;
+      for (int k = 0; k < 9; ++k) {
+        const int h = 2 * ho + k / 3 - 1, w = 2 * wo + k % 3 - 1;
+        ok[k] = h >= 0 && h < H && w >= 0 && w < W;
+        if (ok[k]) win[k] = ld8_cached(img + ((size_t)h * W + w) * C);
       }
-    }
-    st8(out + r * C + c0, pack8(best));
-    if (idx_out) {
-      uint2 packed;
-      packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
-      packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
-      *reinterpret_cast<uint2*>(idx_out + r * C + c0) = packed;
+      float best[8];
+      uint32_t bidx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) best[i] = -1.f, bidx[i] = 0;  // relu output >= 0 > -1
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (!ok[k]) continue;
+        float v[8];
+        unpack8(win[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float act = fmaxf(fmaf(v[i], scale[i], shift[i]), 0.f);
+          if (act > best[i]) best[i] = act, bidx[i] = k;
+        }
+      }
+      const size_t o = ((size_t)row * Wo + wo) * C + c0;
+      st8(out + o, pack8(best));
+      if (idx_out) {
+        uint2 packed;
+        packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+        packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+        *reinterpret_cast<uint2*>(idx_out + o) = packed;
+      }
     }
   }
 }
@@ -409,69 +412,74 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, __nv_bfloat16* g_out,
-                                                            float* scratch, int N, int H, int W) {
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ g_out, float* scratch, int N,
+                                                            int H, int W) {
   __shared__ float red[2][256][9];
   const int C = 64, tpr = 8;
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
-  float mu[8], is[8], scale[8], shift[8], s[8], d[8];
+  float scale[8], shift[8], s[8], d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    mu[i] = mean[c0 + i];
-    is[i] = invstd[c0 + i];
-    scale[i] = gamma[c0 + i] * is[i];
-    shift[i] = beta[c0 + i] - mu[i] * scale[i];
+    scale[i] = gamma[c0 + i] * invstd[c0 + i];
+    shift[i] = beta[c0 + i] - mean[c0 + i] * scale[i];
     s[i] = d[i] = 0.f;
   }
   const int Ho = H / 2, Wo = W / 2;
-  const long long M = (long long)N * H * W;
-  for (long long r = (long long)blockIdx.x * 32 + roff; r < M; r += (long long)gridDim.x * 32) {
-    const int w = (int)(r % W);
-    const int h = (int)((r / W) % H);
-    const long long n = r / ((long long)W * H);
-    const bf16x8 yraw = ld8(y + r * C + c0);
-    // windows (ho, wo) with 2ho-1 <= h <= 2ho+1: ho in {h>>1, (h+1)>>1}
-    bf16x8 dp[4];
-    uint2 wi[4];
-    int kpos[4];
-    bool ok[4];
+  // one block iteration = one input row (n, h); windows (ho, wo) with 2ho-1 <= h <= 2ho+1: ho in {h>>1, (h+1)>>1}
+  for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+    const int n = row / H, h = row - n * H;
+    const int ho_a = h >> 1, ho_b = (h + 1) >> 1;
+    const bool has_b = (h & 1) && ho_b < Ho;  // odd rows belong to two windows (if the second one exists)
+    const int krow_a = (h - (2 * ho_a - 1)) * 3, krow_b = (h - (2 * ho_b - 1)) * 3;
+    const size_t pool_a = ((size_t)n * Ho + ho_a) * Wo, pool_b = ((size_t)n * Ho + ho_b) * Wo;
+#pragma unroll 2
+    for (int w = roff; w < W; w += 32) {
+      const size_t o = ((size_t)row * W + w) * C + c0;
+      const bf16x8 yraw = ld8(y + o);
+      const int wo_a = w >> 1, wo_b = (w + 1) >> 1;
+      const bool has_wb = (w & 1) && wo_b < Wo;
+      const int kcol_a = w - (2 * wo_a - 1), kcol_b = w - (2 * wo_b - 1);
+      bf16x8 dp[4];
+      uint2 wi[4];
+      int kpos[4];
+      bool ok[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ho = (q >> 1) ? ((h + 1) >> 1) : (h >> 1);
-      const int wo = (q & 1) ? ((w + 1) >> 1) : (w >> 1);
-      // odd h / w belong to two windows, even ones to a single window
-      ok[q] = ho < Ho && wo < Wo && !((q >> 1) && !(h & 1)) && !((q & 1) && !(w & 1));
-      kpos[q] = (h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1));
-      if (ok[q]) {
-        const long long o = ((n * Ho + ho) * Wo + wo) * C + c0;
-        dp[q] = ld8_cached(dpool + o);
-        wi[q] = *reinterpret_cast<const uint2*>(idx + o);
+      for (int q = 0; q < 4; ++q) {
+        const bool hb = q >> 1, wb = q & 1;
+        ok[q] = (!hb || has_b) && (!wb || has_wb);
+        kpos[q] = (hb ? krow_b : krow_a) + (wb ? kcol_b : kcol_a);
+        if (ok[q]) {
+          const size_t po = ((hb ? pool_b : pool_a) + (wb ? wo_b : wo_a)) * C + c0;
+          dp[q] = ld8_cached(dpool + po);
+          wi[q] = *reinterpret_cast<const uint2*>(idx + po);
+        }
       }
-    }
-    float yv[8], g[8];
-    unpack8(yraw, yv);
+      float yv[8], g[8];
+      unpack8(yraw, yv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (!ok[q]) continue;
-      float dv[8];
-      unpack8(dp[q], dv);
+      for (int q = 0; q < 4; ++q) {
+        if (!ok[q]) continue;
+        float dv[8];
+        unpack8(dp[q], dv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t word = i < 4 ? wi[q].x : wi[q].y;
+          const int win = (word >> (8 * (i & 3))) & 0xFF;
+          g[i] += win == kpos[q] ? dv[i] : 0.f;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint32_t word = i < 4 ? wi[q].x : wi[q].y;
-        const int win = (word >> (8 * (i & 3))) & 0xFF;
-        g[i] += win == kpos[q] ? dv[i] : 0.f;
+        g[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
+        s[i] += g[i];
+        d[i] = fmaf(g[i], yv[i], d[i]);
       }
+      st8(g_out + o, pack8(g));
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      g[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
-      s[i] += g[i];
-      d[i] = fmaf(g[i], yv[i], d[i]);
-    }
-    st8(g_out + r * C + c0, pack8(g));
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
@@ -534,24 +542,25 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 // ---- input transform: two fp32 NCHW view batches -> one zero-padded bf16 NHWC4 batch -----------------
 // out [2B][H + 6][W + 16][4], image pixel (h, w) at (h + 3, w + 3); channel 3 and the border are zero.
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
-                                                         __nv_bfloat16* out, int B, int H, int W) {
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W) {
   const int Hp = H + 6, Wp = W + 16;
-  const long long total = (long long)2 * B * Hp * Wp;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int wp = (int)(t % Wp);
-    const int hp = (int)((t / Wp) % Hp);
-    const int n = (int)(t / ((long long)Wp * Hp));
-    const int h = hp - 3, w = wp - 3;
-    uint2 v = make_uint2(0u, 0u);
-    if (h >= 0 && h < H && w >= 0 && w < W) {
-      const float* src = (n < B ? x1 + (long long)n * 3 * H * W : x2 + (long long)(n - B) * 3 * H * W) +
-                         (long long)h * W + w;
-      const long long cs = (long long)H * W;
-      v.x = pack_bf16x2(src[0], src[cs]);
-      v.y = pack_bf16x2(src[2 * cs], 0.f);
+  const size_t cs = (size_t)H * W;
+  // one block iteration = one padded row (n, hp); threads walk the padded pixels (coalesced plane reads)
+  for (int row = blockIdx.x; row < 2 * B * Hp; row += gridDim.x) {
+    const int n = row / Hp, hp = row - n * Hp;
+    const int h = hp - 3;
+    const bool row_ok = h >= 0 && h < H;
+    const float* src = (n < B ? x1 + (size_t)n * 3 * cs : x2 + (size_t)(n - B) * 3 * cs) + (size_t)(row_ok ? h : 0) * W;
+    uint2* dst = reinterpret_cast<uint2*>(out) + (size_t)row * Wp;
+    for (int wp = threadIdx.x; wp < Wp; wp += 256) {
+      const int w = wp - 3;
+      uint2 v = make_uint2(0u, 0u);
+      if (row_ok && w >= 0 && w < W) {
+        v.x = pack_bf16x2(src[w], src[cs + w]);
+        v.y = pack_bf16x2(src[2 * cs + w], 0.f);
+      }
+      dst[wp] = v;
     }
-    *reinterpret_cast<uint2*>(out + t * 4) = v;
   }
 }
 
@@ -607,7 +616,6 @@ extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sums
   const int kr = elt_rows();
   const int grid = grid_for(M, rows_per_block * kr);
   if (kr == 2) bn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  else if (kr == 8) bn_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   else bn_apply_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return last_error();
 }
@@ -642,7 +650,7 @@ extern "C" int peclr_stem_bn_relu_pool(const void* y, const float* sum, const fl
                                        float* invstd_out, float* running_mean, float* running_var, int N, int H,
                                        int W, float eps, float momentum, void* stream) {
   if ((H & 1) || (W & 1)) return -1001;
-  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2) * (W / 2), 32), 256, 0, (cudaStream_t)stream>>>(
+  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2), 1, 4), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, (uint8_t*)idx_out, mean_out, invstd_out, running_mean,
       running_var, N, H, W, eps, momentum);
   return last_error();
@@ -654,7 +662,7 @@ extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const voi
   if ((H & 1) || (W & 1) || !idx) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * 64 * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
-  stem_pool_bwd_kernel<<<grid_for((long long)N * H * W, 32 * 2), 256, 0, (cudaStream_t)stream>>>(
+  stem_pool_bwd_kernel<<<grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H,
       W);
   return last_error();
@@ -675,7 +683,7 @@ extern "C" int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int
 }
 
 extern "C" int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream) {
-  stem_input_kernel<<<grid_for((long long)2 * B * (H + 6) * (W + 16), 256), 256, 0, (cudaStream_t)stream>>>(
+  stem_input_kernel<<<grid_for((long long)2 * B * (H + 6), 1, 8), 256, 0, (cudaStream_t)stream>>>(
       x1, x2, (bf16*)out, B, H, W);
   return last_error();
 }
