@@ -37,6 +37,13 @@ int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int 
  * weight copy produced by peclr_weight_transpose.  accumulate != 0 adds into dx (TMA reduce-add). */
 int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int accumulate, void* stream);
+/* The same dgrad with the BatchNorm-backward reduction of the BN + ReLU sitting in front of this convolution fused
+ * into the epilogue: bn_y = that BatchNorm's input (shape of dx), bn_* its saved mean / invstd and affine
+ * parameters; scratch[0:Cin] = sum g, scratch[Cin:2Cin] = sum g*y with g = dx * relu'  (what peclr_bn_bwd_reduce
+ * with mask_mode 2 computes in a separate pass).  Follow with peclr_bn_bwd_apply(mask_mode 2). */
+int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                                int k, int stride, const void* bn_y, const float* bn_mean, const float* bn_invstd,
+                                const float* bn_gamma, const float* bn_beta, float* scratch, void* stream);
 /* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x) */
 int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, void* stream);

@@ -19,6 +19,7 @@ SIGNATURES = {
     "peclr_abi_version": [],
     "peclr_conv2d_fprop": [P, P, P, I, I, I, I, I, I, I, P, P, P],
     "peclr_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, P],
+    "peclr_conv2d_dgrad_bnreduce": [P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P],
     "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
     "peclr_stem_wgrad": [P, P, P, I, I, I, P],
@@ -86,7 +87,7 @@ _PROFILE = None
 
 
 def _kernels_in_call(name, args):
-    if name == "peclr_conv2d_dgrad":
+    if name in ("peclr_conv2d_dgrad", "peclr_conv2d_dgrad_bnreduce"):
         return 4 if (args[8] == 3 and args[9] == 2) else 1
     if name == "peclr_lars_adam_step":
         return 2 if args[17] else 1

@@ -79,20 +79,38 @@ extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, 
                           stat_sumsq, 0, st);
 }
 
-extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
-                                  int k, int stride, int accumulate, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// dgrad, optionally with the BatchNorm-backward reduction of the BN (+ReLU) in front of this convolution fused
+// into the epilogue (bn_y = that BN's input, same shape as dx; scratch[0:Cin] += sum g, scratch[Cin:2Cin] += sum g*y)
+static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
+                      int stride, int accumulate, const void* bn_y, const float* bn_mean, const float* bn_invstd,
+                      const float* bn_gamma, const float* bn_beta, float* scratch, cudaStream_t st) {
   if (Cin % 64 || Cout % 64 || (k != 1 && k != 3)) return PECLR_ERR_ARG;
+  if (bn_y && (accumulate || !scratch || Cin > 2048)) return PECLR_ERR_ARG;
   const int Ho = H / stride, Wo = W / stride;
   TapTable taps;
   memset(&taps, 0, sizeof(taps));
   View4 a;
   const int64_t ktot = (int64_t)k * k * Cout;
+  float* s_sum = bn_y ? scratch : nullptr;
+  float* s_sq = bn_y ? scratch + Cin : nullptr;
+  if (bn_y) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)Cin * 4, st);
+    if (e != cudaSuccess) return -(int)e;
+  }
+  // the y tile of a launch sits at the same offset from bn_y as the output view does from dx
+  auto bnr_for = [&](const View4& d, BnReduce* store) -> const BnReduce* {
+    if (!bn_y) return nullptr;
+    const ptrdiff_t off = static_cast<const char*>(d.ptr) - static_cast<const char*>(dx);
+    *store = BnReduce{static_cast<const char*>(bn_y) + off, bn_mean, bn_invstd, bn_gamma, bn_beta};
+    return store;
+  };
+  BnReduce br;
   if (stride == 1) {
     if (k == 1) {
       a = flat_view(dy, (int64_t)N * H * W, Cout);
       View4 d = flat_view(dx, (int64_t)N * H * W, Cin);
-      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, accumulate, st);
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, s_sum, s_sq, accumulate, st,
+                              bnr_for(d, &br));
     }
     a = nhwc_view(dy, N, H, W, Cout);
     int t = 0;
@@ -103,11 +121,13 @@ extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int 
         taps.koff[t] = t * Cout;
       }
     View4 d = nhwc_view(dx, N, H, W, Cin);
-    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, nullptr, nullptr, accumulate, st);
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, accumulate, st,
+                            bnr_for(d, &br));
   }
   if (stride != 2 || (H & 1) || (W & 1)) return PECLR_ERR_ARG;
   a = nhwc_view(dy, N, Ho, Wo, Cout);
   if (k == 1) {
+    if (bn_y) return PECLR_ERR_ARG;  // (3/4 of dx is plain zero here; no caller needs the fusion)
     // only the even/even pixels of dx receive gradient
     if (!accumulate) {
       cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, st);
@@ -132,10 +152,26 @@ extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int 
         }
       }
       View4 d = parity_view(dx, N, H, W, Cin, ph, pw);
-      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, nullptr, nullptr, accumulate, st);
+      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, s_sum, s_sq, accumulate, st,
+                                bnr_for(d, &br));
       if (rc) return rc;
     }
   return 0;
+}
+
+extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                                  int k, int stride, int accumulate, void* stream) {
+  return dgrad_impl(dy, wt, dx, N, H, W, Cin, Cout, k, stride, accumulate, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
+                                           int Cout, int k, int stride, const void* bn_y, const float* bn_mean,
+                                           const float* bn_invstd, const float* bn_gamma, const float* bn_beta,
+                                           float* scratch, void* stream) {
+  if (!bn_y || !bn_mean || !bn_invstd || !bn_gamma || !bn_beta) return PECLR_ERR_ARG;
+  return dgrad_impl(dy, wt, dx, N, H, W, Cin, Cout, k, stride, 0, bn_y, bn_mean, bn_invstd, bn_gamma, bn_beta, scratch,
+                    static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,

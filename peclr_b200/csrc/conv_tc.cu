@@ -47,6 +47,11 @@ struct GemmParams {
   float* stat_sum;
   float* stat_sumsq;
   int reduce_add;
+  // fused BatchNorm-backward reduction (dgrad feeding an inner BN + ReLU): with y = that BN's input tile,
+  // g = D * [fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0]; stat_sum += sum g, stat_sumsq += sum g*y
+  CUtensorMap y_map;
+  const float *bn_mean, *bn_invstd, *bn_gamma, *bn_beta;
+  int bn_reduce;
 };
 
 // CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
@@ -61,11 +66,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kStageA;
   uint8_t* sD = sB + STAGES * kStageB;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sD + (BN / 64) * kStageA);
+  uint8_t* sY = sD + (BN / 64) * kStageA;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sY + (p.bn_reduce ? (BN / 64) * kStageA : 0));
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ybar + 2);
   float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][cout] when stats are requested
 
   const int warp = threadIdx.x >> 5;
@@ -86,6 +93,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8 * CTAS);  // one arrival per epilogue warp (of both CTAs: the leader's barrier)
+        mbar_init(&ybar[i], 1);
       }
       fence_barrier_init();
     }
@@ -112,7 +120,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = first_tile; t < total_tiles; t += tile_step) {
+      int tile_no = 0;
+      for (int t = first_tile; t < total_tiles; t += tile_step, ++tile_no) {
         const int nt = t % p.n_tiles;
         const int mt = (t / p.n_tiles) * CTAS + cta_rank;  // may be one past the end: all-OOB boxes (zero fill)
         const int w0 = (mt % p.tiles_w) * p.Wb;
@@ -141,6 +150,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               phase ^= 1;
             }
           }
+        }
+        if (p.bn_reduce) {  // this tile's BN input, for the epilogue (own CTA, own barrier)
+          mbar_wait(&ybar[1], (tile_no & 1) ^ 1);
+          mbar_expect_tx(&ybar[0], (BN / 64) * kStageA);
+#pragma unroll
+          for (int bx = 0; bx < BN / 64; ++bx)
+            tma_load_4d(&p.y_map, &ybar[0], sY + bx * kStageA, nt * BN + bx * 64, w0, h0, n0);
         }
       }
     }
@@ -244,7 +260,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         const int col = pair * 2;
         const int c16 = (col & 63) >> 3;
         const uint32_t base = sD32 + (col >> 6) * kStageA + ((col & 7) << 1) + rg * kRowsPer * 128;
+        const uint32_t ydelta = smem_u32(sY) - sD32;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
+        float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
+        if (p.bn_reduce) {
+          const int ch = nt * BN + col;
+          sc0 = p.bn_gamma[ch] * p.bn_invstd[ch];
+          sh0 = p.bn_beta[ch] - p.bn_mean[ch] * sc0;
+          sc1 = p.bn_gamma[ch + 1] * p.bn_invstd[ch + 1];
+          sh1 = p.bn_beta[ch + 1] - p.bn_mean[ch + 1] * sc1;
+          mbar_wait(&ybar[0], it & 1);
+        }
         // rows of a box that hangs over the image edge are clipped by the TMA store: keep them out of the
         // statistics too (their taps can still reach valid pixels, so they are not zero)
         const bool edge = w0 + p.Wb > p.d_w || h0 + p.Hb > p.d_h || n0 + p.Nb > p.d_n;
@@ -261,6 +287,22 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) v[j] = 0u;
             }
           }
+          if (p.bn_reduce) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = lds_u32(base + ydelta + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float y0 = bf16_lo(u[j]), y1 = bf16_hi(u[j]), y2 = bf16_lo(u[j + 1]), y3 = bf16_hi(u[j + 1]);
+              const float a0 = fmaf(y0, sc0, sh0) > 0.f ? bf16_lo(v[j]) : 0.f;
+              const float b0 = fmaf(y1, sc1, sh1) > 0.f ? bf16_hi(v[j]) : 0.f;
+              const float a1 = fmaf(y2, sc0, sh0) > 0.f ? bf16_lo(v[j + 1]) : 0.f;
+              const float b1 = fmaf(y3, sc1, sh1) > 0.f ? bf16_hi(v[j + 1]) : 0.f;
+              s0 += a0, s1 += b0, s2 += a1, s3 += b1;
+              q0 = fmaf(a0, y0, q0), q1 = fmaf(b0, y1, q1), q2 = fmaf(a1, y2, q2), q3 = fmaf(b1, y3, q3);
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
             const float a0 = bf16_lo(v[j]), b0 = bf16_hi(v[j]);
@@ -274,6 +316,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         red_shared_add_f32(ss + 4, s1 + s3);
         red_shared_add_f32(ss + p.cout * 4, q0 + q2);
         red_shared_add_f32(ss + p.cout * 4 + 4, q1 + q3);
+        if (p.bn_reduce) {  // every thread is done with the y tile: hand the buffer back to the producer
+          named_bar_sync(2, 256);
+          if (et == 0) mbar_arrive(&ybar[1]);
+        }
       }
     }
     if (et == 0) tma_wait_group0();
@@ -558,8 +604,8 @@ static int sm_count() {
 
 template <int BN, int STAGES, int CTAS>
 static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) + (size_t)(BN / 64) * kStageA + 256 +
-                      (stats ? 2 * (size_t)p.cout * 4 : 0);
+  const size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) +
+                      (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256 + (stats ? 2 * (size_t)p.cout * 4 : 0);
   auto kern = conv_gemm_kernel<BN, STAGES, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
@@ -595,7 +641,7 @@ static bool use_cta_pairs() {
 
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
                      const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
-                     float* stat_sumsq, int reduce_add, cudaStream_t stream) {
+                     float* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr) {
   if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
   if (nout % 64 != 0 || ktot % 64 != 0 || d_view.c != nout) return PECLR_ERR_ARG;
   if (stat_sum && nout > 2048) return PECLR_ERR_ARG;
@@ -606,7 +652,16 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   int rc;
   for (int i = 0; i < kMaxViews; ++i)
     if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
-  const int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+  int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+  if (bnr) {
+    if (!stat_sum || !stat_sumsq || reduce_add) return PECLR_ERR_ARG;
+    if (BN > 128) BN = 128;  // room for the y tile in shared memory
+    View4 yv = d_view;
+    yv.ptr = bnr->y;
+    if ((rc = encode_view(&p.y_map, yv, bw, bh, bn))) return rc;
+    p.bn_mean = bnr->mean, p.bn_invstd = bnr->invstd, p.bn_gamma = bnr->gamma, p.bn_beta = bnr->beta;
+    p.bn_reduce = 1;
+  }
   const bool pairs = use_cta_pairs() && d_view.w * d_view.h * d_view.n > 128;  // at least two m tiles
   if ((rc = encode_matrix(&p.b_map, w, ktot, nout, pairs ? BN / 2 : BN))) return rc;
   if ((rc = encode_view(&p.d_map, d_view, bw, bh, bn))) return rc;

@@ -32,10 +32,17 @@ struct TapTable {
 
 void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn);
 
+// Fused BatchNorm-backward reduction in the epilogue: y = input of the BatchNorm (+ReLU) whose output gradient this
+// GEMM produces (same geometry as D); stat_sum / stat_sumsq then receive sum g and sum g*y per channel.
+struct BnReduce {
+  const void* y;
+  const float *mean, *invstd, *gamma, *beta;
+};
+
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
                      const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
-                     float* stat_sumsq, int reduce_add, cudaStream_t stream);
+                     float* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr);
 
 // dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin)
 int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,

@@ -43,6 +43,7 @@ class StepEngine:
         self._epoch = 0
         self._ws = {}
         self.overlap_wgrad = os.environ.get("PECLR_OVERLAP_WGRAD", "1") != "0"
+        self.fuse_bn_reduce = os.environ.get("PECLR_FUSE_BN_REDUCE", "1") != "0"
         self._side = None
 
     # ------------------------------------------------------------------ parameter arena
@@ -384,10 +385,17 @@ class StepEngine:
             for i in range(len(convs) - 1, 0, -1):
                 conv, bn, x, y, act, sv = convs[i]
                 pconv, pbn, px, py, pact, psv = convs[i - 1]
-                dx = ops.conv2d_dgrad(dy, self._wt(conv), tuple(x.shape), conv.k, conv.stride)
-                # inner BN + ReLU: the mask is recomputed from y (no read of the stored activation)
+                # inner BN + ReLU: the ReLU mask is recomputed from y (no read of the stored activation) and the
+                # reduction pass of the BN backward runs inside the dgrad epilogue
+                fused = self.fuse_bn_reduce and not (conv.k == 1 and conv.stride == 2)
+                if fused:
+                    dx = ops.conv2d_dgrad_bnreduce(dy, self._wt(conv), tuple(x.shape), conv.k, conv.stride, py, psv,
+                                                   self._p(pbn, "weight"), self._p(pbn, "bias"), scratch)
+                else:
+                    dx = ops.conv2d_dgrad(dy, self._wt(conv), tuple(x.shape), conv.k, conv.stride)
                 dy = ops.bn_backward(dx, None, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
-                                     self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"))
+                                     self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"),
+                                     reduce_done=fused)
                 wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(px, dy, pconv.k, pconv.stride,
                                                                          dw=self._g(pconv, "weight")), px, dy)
             conv1 = convs[0][0]

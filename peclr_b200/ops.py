@@ -44,6 +44,18 @@ def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False):
     return dx
 
 
+def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta, scratch, out=None):
+    """dgrad whose epilogue also accumulates the BatchNorm-backward sums of the BN + ReLU in front of the conv
+    (scratch [2*Cin] fp32: sum g, sum g*y).  Follow with bn_backward(..., scratch=scratch, reduce_done=True)."""
+    _need_cuda(dy, wt, bn_y)
+    n, h, wd, cin = in_shape
+    cout = dy.shape[-1]
+    dx = out if out is not None else torch.empty(in_shape, dtype=bf16, device=dy.device)
+    _lib.call("peclr_conv2d_dgrad_bnreduce", dy, wt, dx, n, h, wd, cin, cout, k, stride, bn_y, saved[0], saved[1],
+              gamma, beta, scratch, _s())
+    return dx
+
+
 def conv2d_wgrad(x, dy, k, stride, dw=None):
     """dw [Cout,k*k,Cin] fp32 += dy^T im2col(x)."""
     _need_cuda(x, dy)
@@ -121,7 +133,7 @@ def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=No
 
 
 def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratch=None, dy=None, g_out=None,
-                beta=None):
+                beta=None, reduce_done=False):
     """BatchNorm(+ReLU) backward.  ReLU mask: `mask` tensor (activation > 0) if given, else recomputed from y when
     `beta` is given, else none (dout already masked).  dgamma/dbeta are accumulated in place.  Returns dy[, g]."""
     c = y.shape[-1]
@@ -133,7 +145,8 @@ def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratc
     dy = dy if dy is not None else torch.empty_like(y)
     if want_g and g_out is None:
         g_out = torch.empty_like(y)
-    _lib.call("peclr_bn_bwd_reduce", dout, mask, y, saved[0], saved[1], gamma, beta, mode, scratch, m, c, _s())
+    if not reduce_done:  # (the sums may already come from a dgrad epilogue: conv2d_dgrad_bnreduce)
+        _lib.call("peclr_bn_bwd_reduce", dout, mask, y, saved[0], saved[1], gamma, beta, mode, scratch, m, c, _s())
     _lib.call("peclr_bn_bwd_apply", dout, mask, y, saved[0], saved[1], gamma, beta, mode, scratch, dy, g_out,
               dgamma, dbeta, m, c, _s())
     return (dy, g_out) if want_g else dy

@@ -366,3 +366,31 @@ def test_weight_transpose_and_cast(ops):
     out = torch.empty(flat.numel(), dtype=torch.bfloat16, device="cuda")
     _lib.call("peclr_cast_bf16", flat, out, flat.numel(), _lib.stream_ptr())
     assert torch.equal(out, flat.bfloat16())
+
+
+@pytest.mark.parametrize("case", [(4, 8, 8, 64, 256, 1, 1), (2, 14, 14, 128, 128, 3, 1), (4, 16, 16, 128, 128, 3, 2),
+                                  (32, 14, 14, 256, 256, 3, 1), (3, 8, 8, 512, 128, 1, 1)])
+def test_dgrad_with_fused_bn_reduce(ops, case):
+    """The dgrad epilogue's fused BatchNorm-backward sums equal the separate reduce pass on the same dx."""
+    from peclr_b200 import _lib
+
+    n, h, w, cin, cout, k, s = case
+    x, wt = _conv_data(case, 7)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    dy = nhwc(torch.randn(n, cout, h // s, w // s, device="cuda", generator=g).bfloat16())
+    wt_t = krsc(wt).permute(2, 1, 0).contiguous()
+    y_prev = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()  # input of the BN in front of the conv
+    gamma = torch.rand(cin, device="cuda", generator=g) + 0.5
+    beta = torch.randn(cin, device="cuda", generator=g) * 0.5
+    yf = y_prev.float().reshape(-1, cin)
+    saved = torch.stack([yf.mean(0), torch.rsqrt(yf.var(0, unbiased=False) + 1e-5)])
+    plain = ops.conv2d_dgrad(dy, wt_t, (n, h, w, cin), k, s)
+    scratch = torch.full((2 * cin,), 123.0, device="cuda")
+    fused = ops.conv2d_dgrad_bnreduce(dy, wt_t, (n, h, w, cin), k, s, y_prev, saved, gamma, beta, scratch)
+    ref = torch.empty(2 * cin, device="cuda")
+    _lib.call("peclr_bn_bwd_reduce", plain, None, y_prev, saved[0], saved[1], gamma, beta, 2, ref, n * h * w, cin,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
+    scale = ref.abs().max().item()
+    assert (scratch - ref).abs().max().item() <= 2e-3 * scale, ((scratch - ref).abs().max().item(), scale)
