@@ -653,6 +653,12 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   for (int i = 0; i < kMaxViews; ++i)
     if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
   int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+  static int bn_max = -1;  // tuning knob: PECLR_CONV_BN_MAX caps the tile width (64 / 128 / 256)
+  if (bn_max < 0) {
+    const char* e = getenv("PECLR_CONV_BN_MAX");
+    bn_max = e ? atoi(e) : 256;
+  }
+  if (BN > bn_max && bn_max >= 64) BN = bn_max;
   if (bnr) {
     if (!stat_sum || !stat_sumsq || reduce_add) return PECLR_ERR_ARG;
     if (BN > 128) BN = 128;  // room for the y tile in shared memory

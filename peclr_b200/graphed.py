@@ -3,6 +3,7 @@ launches of a step are submitted with one cudaGraphLaunch instead of one Python 
 
 The captured work is exactly what ``model.training_step(batch, i)`` followed by ``(loss * scale).backward()``
 enqueues on the stream; the optimiser step stays outside (its learning rate / step count change per step)."""
+import os
 from typing import Dict
 
 import torch
@@ -28,7 +29,10 @@ class GraphedStep:
         from . import _lib
 
         before = _lib.LAUNCHES
-        with torch.cuda.graph(self.graph):
+        # capture on a high-priority stream: the critical path (fprop / dgrad / BatchNorm chain) then outranks the
+        # weight-gradient kernels the engine issues on its default-priority side stream
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("PECLR_GRAPH_PRIORITY", "1") != "0" else None
+        with torch.cuda.graph(self.graph, stream=cap):
             out = model.forward_backward(self.static, grad_scale)
         self.kernels_per_replay = _lib.LAUNCHES - before
         self.out = {k: v.detach() for k, v in out.items()}
