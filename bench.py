@@ -228,8 +228,8 @@ def run_ours(args):
     cpu = None
     # (a step is collective when world > 1 -- fused all-gather, gradient all-reduce -- so every rank runs it)
     prof = _lib.profile_calls(lambda: eager_step(resident[0]),
-                              {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_wgrad",
-                               "peclr_stem_fprop", "peclr_stem_wgrad"})
+                              {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_dgrad_bnreduce",
+                               "peclr_conv2d_wgrad", "peclr_stem_fprop", "peclr_stem_wgrad"})
     if rank == 0:
         pk = peaks()
         flops = {"gemm": 0.0, "wgrad": 0.0}
