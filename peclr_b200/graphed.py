@@ -37,6 +37,9 @@ class GraphedStep:
         self.kernels_per_replay = _lib.LAUNCHES - before
         self.out = {k: v.detach() for k, v in out.items()}
 
+    def matches(self, batch: Dict[str, torch.Tensor]) -> bool:
+        return all(k in batch and batch[k].shape == v.shape for k, v in self.static.items())
+
     def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Copies the batch into the captured input buffers and replays the step.  The returned tensors are the
         graph's static outputs (valid until the next replay)."""
@@ -44,6 +47,8 @@ class GraphedStep:
 
         for k, dst in self.static.items():
             src = batch[k]
+            if src.shape != dst.shape:
+                raise ValueError(f"GraphedStep was captured for {k} of shape {tuple(dst.shape)}, got {tuple(src.shape)}")
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()

@@ -185,8 +185,12 @@ class Trainer:
 
                         graphed = GraphedStep(model, batch, grad_scale=1.0 / acc)
                         opt.zero_grad()
-                    out = graphed(batch)
-                    outputs.append({k: v.clone() for k, v in out.items()})
+                    if graphed.matches(batch):
+                        out = graphed(batch)
+                        outputs.append({k: v.clone() for k, v in out.items()})
+                    else:  # e.g. a short last batch: same kernels, submitted eagerly
+                        out = model.forward_backward(batch, 1.0 / acc)
+                        outputs.append({k: v.detach() for k, v in out.items()})
                 else:
                     model.train_metrics = {}
                     out = model.training_step(batch, batch_idx)
