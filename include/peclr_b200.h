@@ -48,10 +48,10 @@ int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N,
 int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, void* stream);
 /* 7x7/stride 2/pad 3 stem (features.0).  xpad = [N][H+6][W+16][4] bf16 from peclr_stem_input,
- * wpack = [64][4][2*8*4] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
+ * wpack = [64][7][16*4] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
 int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
                      float* stat_sumsq, void* stream);
-/* dwpack[64][4][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
+/* dwpack[64][7][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
 int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream);
 
 /* ---- HBM-bound trunk kernels (csrc/bn_act.cu) --------------------------------------------------------

@@ -196,19 +196,21 @@ extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int 
 
 // ---- 7x7 / stride 2 / pad 3 stem on a zero-padded NHWC4 image ------------------------------------
 // xpad: [N][H + 6][W + 16][4] bf16, pixel (h, w) of the image at (h + 3, w + 3), everything else 0.
-// For output (ho, wo) and filter-row pair kb (rows 2kb, 2kb + 1) the two 8-pixel windows starting at padded pixels
-// (2ho + 2kb + j, 2wo), j = 0, 1, are 2 x 32 contiguous bf16: a rank-5 TMA view (32, 2, Wo, Ho + 3, N) with
-// overlapping strides lays them out as one 128-byte K-major operand row.  K = 4 row pairs x 64 = 256
-// (taps s = 7, row 7 and channel 3 carry zero weights).  Weights: [64][4][2 * 8 * 4] bf16.
+// For output (ho, wo) and filter row r the 16-pixel window starting at padded pixel (2ho + r, 2wo) is
+// 64 contiguous bf16: that window is the "channel" dimension of an ordinary K-major GEMM operand.
+// Weights: [64][7][16 * 4] bf16 (taps s >= 7 and channel 3 are zero), K = 448.
 static void stem_views(const void* xpad, int N, int H, int W, View4* views, TapTable* taps) {
   const int64_t Hp = H + 6, Wp = W + 16;
   memset(taps, 0, sizeof(*taps));
-  views[0] = View4{xpad, 32, W / 2, H / 2 + 3, N, 8, 2 * Wp * 4, Hp * Wp * 4, 2, Wp * 4};
-  for (int kb = 0; kb < 4; ++kb) {
-    taps->view[kb] = 0;
-    taps->dh[kb] = (int8_t)kb;
-    taps->dw[kb] = 0;
-    taps->koff[kb] = kb * 64;
+  for (int pr = 0; pr < 2; ++pr) {
+    const char* base = static_cast<const char*>(xpad) + (int64_t)pr * Wp * 4 * 2;
+    views[pr] = View4{base, 64, W / 2, Hp / 2, N, 8, 2 * Wp * 4, Hp * Wp * 4};
+  }
+  for (int r = 0; r < 7; ++r) {
+    taps->view[r] = (int8_t)(r & 1);
+    taps->dh[r] = (int8_t)(r >> 1);
+    taps->dw[r] = 0;
+    taps->koff[r] = r * 64;
   }
 }
 
@@ -219,7 +221,7 @@ extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, in
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0,
+  return conv_gemm_launch(views, 2, wpack, 7 * 64, 64, d, taps, 7, 1, stat_sum, stat_sumsq, 0,
                           static_cast<cudaStream_t>(stream));
 }
 
@@ -229,5 +231,5 @@ extern "C" int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack,
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{dy, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_wgrad_launch(views, 1, d, taps, 4, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
+  return conv_wgrad_launch(views, 2, d, taps, 7, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
 }

@@ -52,7 +52,6 @@ struct GemmParams {
   CUtensorMap y_map;
   const float *bn_mean, *bn_invstd, *bn_gamma, *bn_beta;
   int bn_reduce;
-  int a_rank5;  // the A views are rank-5 maps (stem windows): coordinates (0, 0, w, h, n)
 };
 
 // CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
@@ -138,14 +137,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             if constexpr (CTAS == 2) {
               // both CTAs' bytes are counted on the leader's barrier
               if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * (kStageA + kStageB));
-              if (p.a_rank5) tma_load_5d_2sm(amap, &full[stage], sA + stage * kStageA, 0, 0, cw, ch, n0);
-              else tma_load_4d_2sm(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
+              tma_load_4d_2sm(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
               tma_load_2d_2sm(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64,
                               nt * BN + cta_rank * (BN / 2));
             } else {
               mbar_expect_tx(&full[stage], kStageA + kStageB);
-              if (p.a_rank5) tma_load_5d(amap, &full[stage], sA + stage * kStageA, 0, 0, cw, ch, n0);
-              else tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
+              tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
               tma_load_2d(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64, nt * BN);
             }
             if (++stage == STAGES) {
@@ -354,7 +351,6 @@ struct WgradParams {
   TapTable taps;
   int num_taps, taps_per_unit, tap_groups;
   int pair_taps;     // Cin == 64: the two 64-channel halves of the 128-row operand hold two different filter taps
-  int x_rank5;       // the X views are rank-5 maps (stem windows): coordinates (0, 0, w, h, n)
   int group_over_m;  // 1x1 filters: the G accumulators of a unit are G consecutive 128-channel m tiles (tap 0)
   int m_tiles, n_tiles, ksplit;
   int tiles_w, tiles_h, tiles_n;
@@ -441,12 +437,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
             for (int b = 0; b < 2; ++b) {
               const int tap = 2 * (tap0 + g) + b;
               if (tap >= p.num_taps) break;
-              if (p.x_rank5)
-                tma_load_5d(&p.x_maps[p.taps.view[tap]], &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, 0,
-                            0, w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
-              else
-                tma_load_4d(&p.x_maps[p.taps.view[tap]], &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, 0,
-                            w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
+              tma_load_4d(&p.x_maps[p.taps.view[tap]], &full[stage], st + kBBytes + g * kABytes + b * kBoxBytes, 0,
+                          w0 + p.taps.dw[tap], h0 + p.taps.dh[tap], n0);
             }
             continue;
           }
@@ -541,30 +533,22 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 view (C, [R2,] W, H, N) with C contiguous; strides in elements; box (min(C, 64), [R2,] bw, bh, bn); 128B swizzle.
+// rank-4 bf16 view (C, W, H, N); strides in elements for W, H, N; box (64, bw, bh, bn); 128B swizzle.
 static int encode_view(CUtensorMap* m, const View4& v, int bw, int bh, int bn) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return PECLR_ERR_DRIVER;
-  cuuint64_t dims[5];
-  cuuint64_t strides[4];
-  cuuint32_t box[5];
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  int rank = 0;
-  dims[rank] = (cuuint64_t)v.c, box[rank] = (cuuint32_t)(v.c < 64 ? v.c : 64), ++rank;
-  if (v.r2 > 0) {
-    strides[rank - 1] = (cuuint64_t)v.sr2 * 2;
-    dims[rank] = (cuuint64_t)v.r2, box[rank] = (cuuint32_t)v.r2, ++rank;
-  }
-  strides[rank - 1] = (cuuint64_t)v.sw * 2, dims[rank] = (cuuint64_t)v.w, box[rank] = (cuuint32_t)bw, ++rank;
-  strides[rank - 1] = (cuuint64_t)v.sh * 2, dims[rank] = (cuuint64_t)v.h, box[rank] = (cuuint32_t)bh, ++rank;
-  strides[rank - 1] = (cuuint64_t)v.sn * 2, dims[rank] = (cuuint64_t)v.n, box[rank] = (cuuint32_t)bn, ++rank;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(v.ptr), dims, strides, box, es,
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    fprintf(stderr, "peclr: cuTensorMapEncodeTiled(rank %d) failed: %d dims=(%llu,%llu,%llu,%llu) box=(%d,%d,%d)\n", rank,
-            (int)r, (unsigned long long)v.c, (unsigned long long)v.w, (unsigned long long)v.h, (unsigned long long)v.n,
-            bw, bh, bn);
+    fprintf(stderr, "peclr: cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%d,%d,%d)\n",
+            (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+            (unsigned long long)strides[2], bw, bh, bn);
     return PECLR_ERR_TENSORMAP;
   }
   return 0;
@@ -690,7 +674,6 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.taps = taps;
   p.num_taps = num_taps;
   p.c_chunks = c_chunks;
-  p.a_rank5 = a_views[0].r2 > 0;
   p.Wb = bw, p.Hb = bh, p.Nb = bn;
   p.log_wb = __builtin_ctz(bw);
   p.log_wbhb = __builtin_ctz(bw * bh);
@@ -762,7 +745,6 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   }
   p.n_tiles = cout / BN;
   p.a_boxes = (cin >= 128 || p.pair_taps) ? 2 : 1;
-  p.x_rank5 = x_views[0].r2 > 0;
   p.Wb = bw, p.Hb = bh, p.Nb = bn;
   p.tiles_w = (int)((dy_view.w + bw - 1) / bw);
   p.tiles_h = (int)((dy_view.h + bh - 1) / bh);

@@ -19,9 +19,6 @@ struct View4 {
   const void* ptr;
   int64_t c, w, h, n;
   int64_t sw, sh, sn;
-  // optional extra dimension between C and W (r2 > 0 -> rank-5 map with box (c, r2, bw, bh, bn)): the stem's
-  // "two filter rows x 8 pixels x 4 channels" window, whose 2 x 32 elements form one 128-byte operand row
-  int64_t r2, sr2;
 };
 
 // One entry per filter tap: which view to read, the pixel offset inside that view's lattice and the

@@ -79,12 +79,12 @@ def stem_input(img1, img2, out=None):
 
 
 def stem_pack(w_master, out=None):
-    """(64,3,7,7) fp32 channels_last master -> [64,4,64] bf16 packed stem weights."""
+    """(64,3,7,7) fp32 channels_last master -> [64,7,64] bf16 packed stem weights."""
     assert w_master.shape == (64, 3, 7, 7)
     flat = w_master.permute(0, 2, 3, 1)
     assert flat.is_contiguous(), "stem weight must be stored channels_last"
     if out is None:
-        out = torch.empty((64, 4, 64), dtype=bf16, device=w_master.device)
+        out = torch.empty((64, 7, 64), dtype=bf16, device=w_master.device)
     _lib.call("peclr_stem_pack", flat, out, _s())
     return out
 
@@ -102,7 +102,7 @@ def stem_fprop(xpad, wpack, h, w, want_stats=False, out=None, stats=None):
 def stem_wgrad(xpad, dy, h, w, dwpack=None):
     n = xpad.shape[0]
     if dwpack is None:
-        dwpack = torch.zeros((64, 4, 64), dtype=torch.float32, device=xpad.device)
+        dwpack = torch.zeros((64, 7, 64), dtype=torch.float32, device=xpad.device)
     _lib.call("peclr_stem_wgrad", xpad, dy, dwpack, n, h, w, _s())
     return dwpack
 
