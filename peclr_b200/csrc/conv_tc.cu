@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ybar + 2);
-  float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][cout] when stats are requested
+  // per-CTA statistics, one private copy per row group ([512/BN][2][cout]): every address has exactly one owner
+  // thread, so the per-tile accumulation is a plain read-modify-write (shared fp32 atomics are CAS loops)
+  float* sStat = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     else tmem_alloc<2 * BN>(tmem_slot);
   }
   if (want_stats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 2 * p.cout; i += 256) sStat[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < (512 / BN) * 2 * p.cout; i += 256) sStat[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255
-    const uint32_t sD32 = smem_u32(sD), sStat32 = smem_u32(sStat);
+    const uint32_t sD32 = smem_u32(sD);
     int it = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
@@ -311,11 +313,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             q0 = fmaf(a0, a0, q0), q1 = fmaf(b0, b0, q1), q2 = fmaf(a1, a1, q2), q3 = fmaf(b1, b1, q3);
           }
         }
-        const uint32_t ss = sStat32 + (nt * BN + col) * 4;
-        red_shared_add_f32(ss, s0 + s2);
-        red_shared_add_f32(ss + 4, s1 + s3);
-        red_shared_add_f32(ss + p.cout * 4, q0 + q2);
-        red_shared_add_f32(ss + p.cout * 4 + 4, q1 + q3);
+        float2* mine_s = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + nt * BN + col);
+        float2* mine_q = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + p.cout + nt * BN + col);
+        float2 as = *mine_s, aq = *mine_q;
+        as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
+        *mine_s = as, *mine_q = aq;
         if (p.bn_reduce) {  // every thread is done with the y tile: hand the buffer back to the producer
           named_bar_sync(2, 256);
           if (et == 0) mbar_arrive(&ybar[1]);
@@ -326,7 +328,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     if (want_stats) {
       named_bar_sync(1, 256);
       for (int i = et; i < p.cout; i += 256) {
-        const float s = sStat[i], qq = sStat[p.cout + i];
+        float s = 0.f, qq = 0.f;
+#pragma unroll
+        for (int g = 0; g < 512 / BN; ++g) s += sStat[g * 2 * p.cout + i], qq += sStat[g * 2 * p.cout + p.cout + i];
         if (s != 0.f || qq != 0.f) {
           red_add_f32(p.stat_sum + i, s);
           red_add_f32(p.stat_sumsq + i, qq);
@@ -605,7 +609,8 @@ static int sm_count() {
 template <int BN, int STAGES, int CTAS>
 static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) +
-                      (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256 + (stats ? 2 * (size_t)p.cout * 4 : 0);
+                      (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256 +
+                      (stats ? (size_t)(512 / BN) * 2 * p.cout * 4 : 0);
   auto kern = conv_gemm_kernel<BN, STAGES, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
