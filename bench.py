@@ -161,6 +161,14 @@ def run_ours(args):
     for i in range(args.warmup):
         step(resident[i % 2])
     barrier()
+    if args.ncu_step:
+        # launch-list capture: `ncu --profile-from-start off ... bench.py --ncu-step --no-graph` sees exactly the
+        # launches of ONE step (cudaProfilerStart/Stop); nothing printed under a profiler is a bench value
+        torch.cuda.profiler.start()
+        step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     launches0 = _lib.LAUNCHES
     sampler = ClockSampler(local)
     sampler.start()
@@ -372,6 +380,8 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--ncu-step", dest="ncu_step", action="store_true",
+                    help="run the warm-up, then ONE step between cudaProfilerStart/Stop, and exit (for ncu)")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="submit kernels eagerly (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
