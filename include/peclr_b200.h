@@ -129,6 +129,30 @@ int peclr_ntxent_fused(const float* p, const double* angle, const long long* jx,
 int peclr_ntxent_plain(const float* z, int B, int dim, float temperature, float* loss, float* g_z, void* workspace,
                        long long workspace_bytes, void* stream);
 
+/* ---- the equivariance corrections as stand-alone operators (csrc/equiv_ops.cu), fp32 ------------------
+ * The reference exposes them as free functions that model variants and user code call directly; the training
+ * step itself uses the fused kernel above.  enc is [n][m][d] contiguous, d >= 2; only coordinates 0 and 1 of
+ * every point are touched; all of them work in place. */
+/* translate_encodings (src/models/utils.py:325-346): x += tx*(max_x - min_x), y += ty*(max_y - min_y) with the
+ * per-sample range taken over the m points (detached: the gradient is the identity); exact != 0 gives
+ * translate_encodings2 (:349-364): x += tx, y += ty. */
+int peclr_translate_encodings(float* enc, const float* tx, const float* ty, int n, int m, int d, int exact,
+                              void* stream);
+/* rotate_encoding (src/models/utils.py:301-321): rotation by angle[i] degrees (f64) about the sample's (detached)
+ * mean point with the OpenCV-convention matrix of get_rotation_2D_matrix; rot (optional, float[n][4]) receives
+ * {alpha, beta, off_x, off_y} for the backward pass. */
+int peclr_rotate_encoding(float* enc, const double* angle, float* rot, int n, int m, int d, void* stream);
+/* g[..., :2] <- g[..., :2] @ R[:2,:2]^T, in place (the gradient of rotate_encoding w.r.t. its input) */
+int peclr_rotate_encoding_bwd(float* g, const float* rot, int n, int m, int d, void* stream);
+/* get_rotation_2D_matrix (src/models/utils.py:271-298): out [n][3][2] fp32 from f64 angles (degrees), fp32
+ * centres and a scalar scale; trig and offsets evaluated in f64 and rounded, as the reference does. */
+int peclr_rotation_2d_matrix(const double* angle, const float* center_x, const float* center_y, double scale,
+                             float* out, int n, void* stream);
+
+/* Hybrid2Model.get_projection_stats (hybrid2_model.py:92-106): out8 = batch means of the per-sample
+ * x{mean, lower median, min, max}, y{...} over the m points of enc [n][m][d]. */
+int peclr_projection_stats(const float* enc, float* out8, int n, int m, int d, void* stream);
+
 /* ---- fused LARS-Adam over the flat parameter buffer (csrc/lars_adam.cu); replaces
  * LARSWrapper(torch.optim.Adam).step() as configured by BaseModel.configure_optimizers
  * (src/models/base_model.py:57-104).  seg_begin[num_segs+1] are tensor boundaries, seg_wd the weight

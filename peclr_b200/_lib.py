@@ -38,6 +38,11 @@ SIGNATURES = {
     "peclr_ntxent_workspace_bytes": [I, I],
     "peclr_ntxent_fused": [P, P, P, P, I, I, I, I, I, I, F, P, P, P, P, L, I, I, P, P, P],
     "peclr_ntxent_plain": [P, I, I, F, P, P, P, L, P],
+    "peclr_translate_encodings": [P, P, P, I, I, I, I, P],
+    "peclr_rotate_encoding": [P, P, P, I, I, I, P],
+    "peclr_rotate_encoding_bwd": [P, P, I, I, I, P],
+    "peclr_rotation_2d_matrix": [P, P, P, c_double, P, I, P],
+    "peclr_projection_stats": [P, P, I, I, I, P],
     "peclr_opt_chunk_elems": [],
     "peclr_lars_adam_step": [P, P, P, P, P, P, P, I, P, P, I, P, F, I, F, F, F, I, F, I, F, P],
     "peclr_cast_bf16": [P, P, L, P],

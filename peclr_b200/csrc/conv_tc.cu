@@ -52,6 +52,7 @@ struct GemmParams {
   CUtensorMap y_map;
   const float *bn_mean, *bn_invstd, *bn_gamma, *bn_beta;
   int bn_reduce;
+  int stat_copies;  // 512 / BN private copies of the per-CTA statistics (one owner thread per address), or 1 (atomics)
 };
 
 // CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ybar + 2);
   // per-CTA statistics, one private copy per row group ([512/BN][2][cout]): every address has exactly one owner
-  // thread, so the per-tile accumulation is a plain read-modify-write (shared fp32 atomics are CAS loops)
+  // thread, so the per-tile accumulation is a plain read-modify-write (shared fp32 atomics are CAS loops).  When
+  // the copies do not fit next to the pipeline stages (stat_copies == 1) the threads fall back to shared atomics.
   float* sStat = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     else tmem_alloc<2 * BN>(tmem_slot);
   }
   if (want_stats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < (512 / BN) * 2 * p.cout; i += 256) sStat[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < p.stat_copies * 2 * p.cout; i += 256) sStat[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -313,11 +315,19 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             q0 = fmaf(a0, a0, q0), q1 = fmaf(b0, b0, q1), q2 = fmaf(a1, a1, q2), q3 = fmaf(b1, b1, q3);
           }
         }
-        float2* mine_s = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + nt * BN + col);
-        float2* mine_q = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + p.cout + nt * BN + col);
-        float2 as = *mine_s, aq = *mine_q;
-        as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
-        *mine_s = as, *mine_q = aq;
+        if (p.stat_copies > 1) {
+          float2* mine_s = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + nt * BN + col);
+          float2* mine_q = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + p.cout + nt * BN + col);
+          float2 as = *mine_s, aq = *mine_q;
+          as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
+          *mine_s = as, *mine_q = aq;
+        } else {
+          const uint32_t ss = smem_u32(sStat) + (nt * BN + col) * 4;
+          red_shared_add_f32(ss, s0 + s2);
+          red_shared_add_f32(ss + 4, s1 + s3);
+          red_shared_add_f32(ss + p.cout * 4, q0 + q2);
+          red_shared_add_f32(ss + p.cout * 4 + 4, q1 + q3);
+        }
         if (p.bn_reduce) {  // every thread is done with the y tile: hand the buffer back to the producer
           named_bar_sync(2, 256);
           if (et == 0) mbar_arrive(&ybar[1]);
@@ -329,8 +339,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       named_bar_sync(1, 256);
       for (int i = et; i < p.cout; i += 256) {
         float s = 0.f, qq = 0.f;
-#pragma unroll
-        for (int g = 0; g < 512 / BN; ++g) s += sStat[g * 2 * p.cout + i], qq += sStat[g * 2 * p.cout + p.cout + i];
+        for (int g = 0; g < p.stat_copies; ++g) s += sStat[g * 2 * p.cout + i], qq += sStat[g * 2 * p.cout + p.cout + i];
         if (s != 0.f || qq != 0.f) {
           red_add_f32(p.stat_sum + i, s);
           red_add_f32(p.stat_sumsq + i, qq);
@@ -607,10 +616,17 @@ static int sm_count() {
 }
 
 template <int BN, int STAGES, int CTAS>
-static int launch_gemm_t(const GemmParams& p, bool stats, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) +
-                      (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256 +
-                      (stats ? (size_t)(512 / BN) * 2 * p.cout * 4 : 0);
+static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
+  constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+  size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) +
+                (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256;
+  p.stat_copies = 0;
+  if (stats) {
+    p.stat_copies = 512 / BN;
+    if (smem + (size_t)p.stat_copies * 2 * p.cout * 4 > kMaxSmem) p.stat_copies = 1;
+    smem += (size_t)p.stat_copies * 2 * p.cout * 4;
+  }
+  if (smem > kMaxSmem) return PECLR_ERR_ARG;
   auto kern = conv_gemm_kernel<BN, STAGES, CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;

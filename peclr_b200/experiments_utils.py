@@ -3,7 +3,10 @@ src/experiments/utils.py that peclr_training.py uses: get_general_args :29-163, 
 update_param :317-332, get_model :564-574, get_callbacks :587-605, update_model_params :608-615), plus the
 flags this build adds for synthetic data and multi-GPU runs."""
 import argparse
+import os
 from typing import List
+
+import torch
 
 from .easydict import EasyDict as edict
 from .hybrid2_model import Hybrid2Model
@@ -78,6 +81,44 @@ def update_model_params(model_param: edict, args, data_length: int, train_param:
     model_param.batch_size = train_param.batch_size
     model_param.num_of_mini_batch = train_param.accumulate_grad_batches
     return model_param
+
+
+_NAME_CODES = {"color_drop": "CD", "color_jitter": "CJ", "crop": "C", "cut_out": "CO", "flip": "F",
+               "gaussian_blur": "GB", "random_crop": "RC", "resize": "Re", "rotate": "Ro", "sobel_filter": "SF",
+               "gaussian_noise": "GN"}
+
+
+def prepare_name(prefix: str, train_param: edict, hybrid_naming: bool = False) -> str:
+    """src/experiments/utils.py:335-393: experiment name = prefix + batch size + sorted augmentation codes."""
+    def codes(flags):
+        return "_".join(sorted(_NAME_CODES[k] for k, v in flags.items() if v))
+
+    if hybrid_naming:
+        return (f"{prefix}{train_param.batch_size}_rel_{codes(train_param.pairwise.augmentation_flags)}"
+                f"_con_{codes(train_param.contrastive.augmentation_flags)}")
+    return f"{prefix}{train_param.batch_size}{codes(train_param.augmentation_flags)}"
+
+
+def save_experiment_key(experiment_name: str, experiment_key: str, filename="default.csv"):
+    """src/experiments/utils.py:396-409: appends "<name>,<key>" to $SAVED_META_INFO_PATH/<filename>."""
+    with open(os.path.join(os.environ.get("SAVED_META_INFO_PATH", "."), filename), "a") as f:
+        f.write(f"{experiment_name},{experiment_key}\n")
+
+
+def restore_model(model, experiment_key: str, checkpoint: str = ""):
+    """src/experiments/utils.py:535-546: loads the newest (or the named) checkpoint's state_dict into `model`."""
+    from .model_utils import get_latest_checkpoint
+
+    path = get_latest_checkpoint(experiment_key, checkpoint)
+    print(f"Restoring {path}")
+    model.load_state_dict(torch.load(path, map_location="cpu")["state_dict"])
+    return model
+
+
+def get_checkpoints(experiment_key: str, number: int = 3) -> List[str]:
+    """src/experiments/utils.py:549-561: the last `number` checkpoint file names (reverse lexicographic order)."""
+    base = os.environ.get("SAVED_MODELS_BASE_PATH", "")
+    return sorted(os.listdir(os.path.join(base, experiment_key, "checkpoints")))[::-1][:number]
 
 
 def get_model(experiment_type: str, heatmap_flag: bool, denoiser_flag: bool):

@@ -115,6 +115,12 @@ class JsonlLogger:
             os.makedirs(save_dir, exist_ok=True)
             self._fh = open(os.path.join(save_dir, experiment_name + ".jsonl"), "a")
 
+    def get_key(self) -> str:
+        """Stable identifier of this run (the role of comet's experiment key in save_experiment_key)."""
+        import hashlib
+
+        return hashlib.sha1(f"{self.save_dir}|{self.experiment_name}".encode()).hexdigest()[:32]
+
     def log_metrics(self, metrics: dict, step: Optional[int] = None):
         rec = {"step": step, **{k: float(v) for k, v in metrics.items()}}
         if self._fh:

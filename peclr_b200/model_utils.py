@@ -1,8 +1,11 @@
-"""Hot-path part of the reference's src/models/utils.py: encoder factory and checkpoint path helpers.
+"""Hot-path part of the reference's src/models/utils.py: encoder factory, the op-level loss-chain functions and
+checkpoint path helpers.
 
-The loss-chain ops of that file (vanila_contrastive_loss :154-186, rotate_encoding :301-321,
-translate_encodings :325-346, get_rotation_2D_matrix :271-298) are executed by the fused CUDA kernel
-(csrc/ntxent.cu); `vanila_contrastive_loss` below exposes the NT-Xent part on its own, same signature.
+Inside the training step the loss-chain ops of that file (vanila_contrastive_loss :154-186, rotate_encoding
+:301-321, translate_encodings :325-346, get_rotation_2D_matrix :271-298) are executed by ONE fused CUDA kernel
+(csrc/ntxent.cu).  The functions below expose each of them on its own behind the reference's signature (same
+in-place semantics, same detached statistics, same autograd behaviour), each backed by its own CUDA kernel
+(csrc/ntxent.cu plain mode, csrc/equiv_ops.cu); there is no torch fallback.
 """
 import os
 
@@ -46,6 +49,79 @@ def vanila_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, temperature: flo
     """NT-Xent of SimCLR over the 2N batch (self excluded, positive included), computed by the fused CUDA kernel
     in its plain mode (no normalisation / equivariance correction).  Same contract as the reference function."""
     return _NtXentFunction.apply(z1, z2, temperature)
+
+
+def _points(encoding: torch.Tensor):
+    if encoding.dim() != 3 or encoding.shape[-1] < 2:
+        raise ValueError("encoding must be (batch, points, >=2), got %s" % (tuple(encoding.shape),))
+    if encoding.dtype != torch.float32:
+        raise TypeError("the encodings kernels are fp32 (the reference's rotate_encoding only works in fp32 too)")
+    return encoding.shape
+
+
+class _RotateFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, encoding, angle):
+        n, m, d = encoding.shape
+        out = encoding.detach().contiguous().clone()
+        rot = torch.empty((n, 4), dtype=torch.float32, device=out.device)
+        ops.rotate_encoding_(out, angle, rot)
+        ctx.save_for_backward(rot)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rot,) = ctx.saved_tensors
+        g = grad_out.contiguous().clone()
+        ops.rotate_encoding_bwd_(g, rot)
+        return g, None
+
+
+def get_rotation_2D_matrix(angle: torch.Tensor, center_x: torch.Tensor, center_y: torch.Tensor, scale) -> torch.Tensor:
+    """src/models/utils.py:271-298: (n,3,2) fp32 transposed OpenCV rotation matrices for a batch of angles in
+    degrees.  (The reference allocates the result on the CPU; here it lives on the inputs' CUDA device.)"""
+    return ops.rotation_2d_matrix(angle, center_x, center_y, float(scale))
+
+
+def rotate_encoding(encoding: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
+    """src/models/utils.py:301-321: rotates every sample's 2-D points about their (detached) mean by `angle`
+    degrees; in place on `encoding[..., :2]` and returns `encoding`, like the reference."""
+    _points(encoding)
+    rotated = _RotateFunction.apply(encoding, angle)
+    encoding[..., :2] = rotated[..., :2]
+    return encoding
+
+
+class _TranslateFunction(torch.autograd.Function):
+    """The shift is built from detached statistics (or is a constant), so the gradient is the identity."""
+
+    @staticmethod
+    def forward(ctx, encoding, translate_x, translate_y, exact):
+        out = encoding.detach().contiguous().clone()
+        ops.translate_encodings_(out, translate_x, translate_y, exact)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out, None, None, None
+
+
+def _translate(encoding, translate_x, translate_y, exact):
+    _points(encoding)
+    shifted = _TranslateFunction.apply(encoding, translate_x, translate_y, exact)
+    encoding[..., :2] = shifted[..., :2]
+    return encoding
+
+
+def translate_encodings(encoding: torch.Tensor, translate_x: torch.Tensor, translate_y: torch.Tensor) -> torch.Tensor:
+    """src/models/utils.py:325-346: x += tx * (max_x - min_x), y += ty * (max_y - min_y) per sample (range over the
+    points, detached); in place, returns `encoding`."""
+    return _translate(encoding, translate_x, translate_y, False)
+
+
+def translate_encodings2(encoding: torch.Tensor, translate_x: torch.Tensor, translate_y: torch.Tensor) -> torch.Tensor:
+    """src/models/utils.py:349-364: exact translation x += tx, y += ty; in place, returns `encoding`."""
+    return _translate(encoding, translate_x, translate_y, True)
 
 
 def get_latest_checkpoint(experiment_name: str, checkpoint: str = "") -> str:

@@ -283,6 +283,65 @@ def ntxent_plain(z, temperature=0.5, want_grad=True, workspace=None):
 
 
 # ------------------------------------------------------------------ optimiser plumbing
+# ---- stand-alone equivariance operators (csrc/equiv_ops.cu); reference src/models/utils.py:271-364 -------------
+def _per_sample(v, n, dtype, device, name):
+    v = torch.as_tensor(v, device=device).reshape(-1).to(dtype).contiguous()
+    if v.numel() != n:
+        raise ValueError("%s must hold one value per sample (%d), got %d" % (name, n, v.numel()))
+    return v
+
+
+def translate_encodings_(enc, tx, ty, exact=False):
+    """In place on a contiguous fp32 [n][m][d] tensor."""
+    _need_cuda(enc)
+    assert enc.is_contiguous() and enc.dtype == torch.float32 and enc.dim() == 3
+    n, m, d = enc.shape
+    tx = _per_sample(tx, n, torch.float32, enc.device, "translate_x")
+    ty = _per_sample(ty, n, torch.float32, enc.device, "translate_y")
+    _lib.call("peclr_translate_encodings", enc, tx, ty, n, m, d, 1 if exact else 0, _s())
+    return enc
+
+
+def rotate_encoding_(enc, angle, rot=None):
+    """In place on a contiguous fp32 [n][m][d] tensor; rot (optional fp32 [n][4]) <- {alpha, beta, off_x, off_y}."""
+    _need_cuda(enc)
+    assert enc.is_contiguous() and enc.dtype == torch.float32 and enc.dim() == 3
+    n, m, d = enc.shape
+    angle = _per_sample(angle, n, torch.float64, enc.device, "angle")
+    _lib.call("peclr_rotate_encoding", enc, angle, rot if rot is not None else 0, n, m, d, _s())
+    return enc
+
+
+def rotate_encoding_bwd_(g, rot):
+    _need_cuda(g, rot)
+    assert g.is_contiguous() and g.dtype == torch.float32 and g.dim() == 3 and rot.dtype == torch.float32
+    n, m, d = g.shape
+    _lib.call("peclr_rotate_encoding_bwd", g, rot, n, m, d, _s())
+    return g
+
+
+def rotation_2d_matrix(angle, center_x, center_y, scale=1.0):
+    _need_cuda(center_x)
+    n = center_x.numel()
+    dev = center_x.device
+    angle = _per_sample(angle, n, torch.float64, dev, "angle")
+    cx = _per_sample(center_x.detach(), n, torch.float32, dev, "center_x")
+    cy = _per_sample(center_y.detach(), n, torch.float32, dev, "center_y")
+    out = torch.empty((n, 3, 2), dtype=torch.float32, device=dev)
+    _lib.call("peclr_rotation_2d_matrix", angle, cx, cy, float(scale), out, n, _s())
+    return out
+
+
+def projection_stats(proj):
+    """fp32 [n][m][d] -> fp32 [8]: x{mean, median, min, max}, y{...} (batch means of per-sample statistics)."""
+    _need_cuda(proj)
+    assert proj.dtype == torch.float32 and proj.dim() == 3
+    n, m, d = proj.shape
+    out = torch.empty((8,), dtype=torch.float32, device=proj.device)
+    _lib.call("peclr_projection_stats", proj, out, n, m, d, _s())
+    return out
+
+
 def build_opt_tables(seg_sizes, seg_wd, device):
     """Flat-buffer segment / chunk tables for peclr_lars_adam_step."""
     chunk = _lib.call("peclr_opt_chunk_elems")

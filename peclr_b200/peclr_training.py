@@ -16,8 +16,8 @@ from pprint import pformat
 import torch
 
 from .easydict import EasyDict as edict
-from .experiments_utils import (get_callbacks, get_general_args, get_model, update_model_params,
-                                update_train_params)
+from .experiments_utils import (get_callbacks, get_general_args, get_model, prepare_name, save_experiment_key,
+                                update_model_params, update_train_params)
 from .lightning import JsonlLogger, Trainer, seed_everything
 
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config")
@@ -52,16 +52,16 @@ def main(argv=None):
         print(f"Train parameters {pformat(dict(train_param))}")
     seed_everything(train_param.seed)
 
-    from torch.utils.data import DataLoader
-
-    from .synthetic import SyntheticTwoViewDataset
+    from .synthetic import SyntheticTwoViewDataset, get_train_val_split
 
     num_samples = args.num_samples or 64 * train_param.batch_size * world
     data = SyntheticTwoViewDataset(num_samples, args.image_size, seed=train_param.seed + rank,
-                                   rotate=bool(train_param.augmentation_flags.get("rotate")))
-    train_loader = DataLoader(data, batch_size=train_param.batch_size, num_workers=train_param.num_workers,
-                              pin_memory=True, drop_last=True, shuffle=False,
-                              persistent_workers=train_param.num_workers > 0)
+                                   rotate=bool(train_param.augmentation_flags.get("rotate")),
+                                   train_ratio=train_param.train_ratio)
+    train_loader, val_loader = get_train_val_split(
+        data, batch_size=train_param.batch_size, num_workers=train_param.num_workers, pin_memory=True,
+        drop_last=True, persistent_workers=train_param.num_workers > 0)
+    experiment_name = args.experiment_name or prepare_name(f"{experiment_type}_", train_param, hybrid_naming=False)
 
     model_param = update_model_params(model_param, args, len(data) * world, train_param)
     model_param.augmentation = [k for k, v in train_param.augmentation_flags.items() if v]
@@ -72,11 +72,13 @@ def main(argv=None):
     callbacks = get_callbacks(logging_interval=args.log_interval, experiment_type="hybrid2",
                               save_top_k=args.save_top_k, period=args.save_period)
     save_dir = os.environ.get("SAVED_META_INFO_PATH")
-    logger = JsonlLogger(save_dir, args.experiment_name or "hybrid2") if rank == 0 else None
+    logger = JsonlLogger(save_dir, experiment_name) if rank == 0 else None
+    if args.meta_file is not None and rank == 0:
+        save_experiment_key(experiment_name, logger.get_key(), args.meta_file)
     trainer = Trainer(accumulate_grad_batches=train_param.accumulate_grad_batches, gpus="0", logger=logger,
                       max_epochs=train_param.epochs, precision=train_param.precision, amp_backend="native",
                       limit_train_batches=args.limit_train_batches, **callbacks)
-    trainer.fit(model, train_loader, None)
+    trainer.fit(model, train_loader, val_loader if len(val_loader) > 0 else None)
     if rank == 0:
         loss = float(model.train_metrics_epoch.get("loss", float("nan")))
         print(json.dumps({"epoch_loss": loss, "images_per_sec": trainer.images_per_sec, "world": world}))

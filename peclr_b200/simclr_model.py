@@ -50,8 +50,8 @@ class SimCLR(BaseModel):
         )
 
     # ---- the step --------------------------------------------------------------------------------------
-    def _forward(self, batch: Dict[str, Tensor], want_grad: bool):
-        """trunk -> head -> fused loss kernel.  Returns loss [1], stats [16], g_p (dloss/dp or None), contexts."""
+    def _projections(self, batch: Dict[str, Tensor]):
+        """trunk -> head, plus the per-sample correction parameters of the batch (None when not used)."""
         eng = self.engine
         img1, img2 = batch["transformed_image1"], batch["transformed_image2"]
         training = self.training
@@ -65,8 +65,12 @@ class SimCLR(BaseModel):
             jy = torch.cat((batch["jitter_y_1"], batch["jitter_y_2"])).to(torch.int64)
         if rotate:
             angle = torch.cat((batch["angle_1"], batch["angle_2"])).to(torch.float64)
-        loss, stats, g_p = eng.forward_loss(p, angle, jx, jy, tuple(img1.shape[-2:]), crop, rotate,
-                                            temperature=0.5, want_grad=want_grad)
+        return p, (angle, jx, jy, tuple(img1.shape[-2:]), crop, rotate), head_ctx, trunk_ctx
+
+    def _forward(self, batch: Dict[str, Tensor], want_grad: bool):
+        """trunk -> head -> fused loss kernel.  Returns loss [1], stats [16], g_p (dloss/dp or None), contexts."""
+        p, corr, head_ctx, trunk_ctx = self._projections(batch)
+        loss, stats, g_p = self.engine.forward_loss(p, *corr, temperature=0.5, want_grad=want_grad)
         return loss, stats, g_p, head_ctx, trunk_ctx
 
     def _run_step(self, batch: Dict[str, Tensor], want_stats: bool):

@@ -6,11 +6,12 @@ Data_Set.prepare_hybrid2_sample + default collate (src/data_loader/data_set.py:3
     angle_1/2             float64 (B,), integer valued in [-45, 45)
     jitter_x_1/2, jitter_y_1/2   int64 (B,), in {-14..0}
 """
-from typing import Dict
+import copy
+from typing import Dict, Tuple
 
 import torch
 import torch.nn.functional as F
-from torch.utils.data import Dataset
+from torch.utils.data import DataLoader, Dataset
 
 
 def synthetic_batch(batch_size: int, size: int, seed: int = 5, structured: bool = True,
@@ -43,13 +44,27 @@ def synthetic_batch(batch_size: int, size: int, seed: int = 5, structured: bool 
 class SyntheticTwoViewDataset(Dataset):
     """Per-sample version for a DataLoader: item i is deterministic in (seed, i)."""
 
-    def __init__(self, num_samples: int, size: int, seed: int = 5, structured: bool = True, rotate: bool = True):
+    def __init__(self, num_samples: int, size: int, seed: int = 5, structured: bool = True, rotate: bool = True,
+                 train_ratio: float = 1.0):
         self.num_samples, self.size, self.seed, self.structured, self.rotate = num_samples, size, seed, structured, rotate
+        # train / validation split with the reference's interface (Data_Set.is_training, data_set.py:386-398; the
+        # FreiHAND loader draws the split with train_test_split(train_size=train_ratio, random_state=seed),
+        # freihand_loader.py:46-60).  Synthetic samples are i.i.d. in their index, so a contiguous split is
+        # equivalent: the first round(train_ratio * N) indices train, the rest validate.
+        self.num_train = min(num_samples, int(round(train_ratio * num_samples)))
+        self._training = True
+
+    def is_training(self, value: bool):
+        self._training = bool(value)
 
     def __len__(self):
-        return self.num_samples
+        return self.num_train if self._training else self.num_samples - self.num_train
 
     def __getitem__(self, idx):
+        if not 0 <= idx < len(self):
+            raise IndexError(idx)
+        if not self._training:
+            idx += self.num_train
         b = synthetic_batch(1, self.size, seed=self.seed * 1000003 + idx, structured=self.structured)
         out = {}
         for k, v in b.items():
@@ -57,3 +72,12 @@ class SyntheticTwoViewDataset(Dataset):
                 continue  # prepare_hybrid2_sample drops None entries (data_set.py:382-383)
             out[k] = v[0] if v.dim() > 1 else (float(v[0]) if v.dtype == torch.float64 else int(v[0]))
         return out
+
+
+def get_train_val_split(data: SyntheticTwoViewDataset, **kwargs) -> Tuple[DataLoader, DataLoader]:
+    """src/data_loader/utils.py:225-275 (single-dataset branch): the training loader shuffles, the validation
+    loader serves a shallow copy of the data set switched to its validation indices."""
+    data.is_training(True)
+    val_data = copy.copy(data)
+    val_data.is_training(False)
+    return (DataLoader(data, **{**kwargs, "shuffle": True}), DataLoader(val_data, **{**kwargs, "shuffle": False}))

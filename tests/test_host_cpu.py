@@ -118,3 +118,51 @@ def test_src_compat_imports():
     from src.models.unsupervised.hybrid2_model import Hybrid2Model
 
     assert get_model("hybrid2", False, False) is Hybrid2Model and callable(peclr_to_torchvision)
+
+
+def test_experiment_naming_and_checkpoint_helpers(model, tmp_path, monkeypatch):
+    """prepare_name / save_experiment_key / get_checkpoints / restore_model (src/experiments/utils.py:335-561)."""
+    from peclr_b200.easydict import EasyDict
+    from src.experiments.utils import get_checkpoints, prepare_name, restore_model, save_experiment_key
+
+    flags = {"color_drop": False, "color_jitter": True, "crop": True, "cut_out": False, "gaussian_blur": False,
+             "random_crop": False, "resize": True, "rotate": True, "gaussian_noise": False, "sobel_filter": False}
+    train = EasyDict(batch_size=128, augmentation_flags=flags)
+    assert prepare_name("hybrid2_", train, hybrid_naming=False) == "hybrid2_128C_CJ_Re_Ro"  # sorted codes
+    both = EasyDict(batch_size=64, pairwise={"augmentation_flags": {"crop": True, "rotate": True}},
+                    contrastive={"augmentation_flags": {"color_jitter": True}})
+    assert prepare_name("hybrid1_", both, hybrid_naming=True) == "hybrid1_64_rel_C_Ro_con_CJ"
+
+    monkeypatch.setenv("SAVED_META_INFO_PATH", str(tmp_path))
+    monkeypatch.setenv("SAVED_MODELS_BASE_PATH", str(tmp_path))
+    save_experiment_key("hybrid2_128C_Ro", "abc123", "meta.csv")
+    save_experiment_key("hybrid2_128C_Ro", "def456", "meta.csv")
+    assert (tmp_path / "meta.csv").read_text() == "hybrid2_128C_Ro,abc123\nhybrid2_128C_Ro,def456\n"
+
+    ckpt_dir = tmp_path / "abc123" / "checkpoints"
+    ckpt_dir.mkdir(parents=True)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["projection_head.3.weight"] = torch.full_like(sd["projection_head.3.weight"], 0.5)
+    for epoch in (2, 10):
+        torch.save({"state_dict": sd, "epoch": epoch}, ckpt_dir / f"epoch={epoch}.ckpt")
+    assert get_checkpoints("abc123", number=1) == ["epoch=2.ckpt"]  # reverse lexicographic, as in the reference
+    restored = restore_model(model, "abc123")  # newest by the integer in the name: epoch=10
+    assert restored is model and float(model.projection_head[3].weight.flatten()[0]) == 0.5
+    assert float(model.engine.flat[model.engine._seg(model.projection_head[3]).begin]) == 0.5  # flat buffer followed
+
+
+def test_synthetic_train_val_split():
+    from peclr_b200.synthetic import SyntheticTwoViewDataset, get_train_val_split
+
+    data = SyntheticTwoViewDataset(100, 16, seed=5, train_ratio=0.9)
+    train, val = get_train_val_split(data, batch_size=8, num_workers=0, drop_last=True)
+    assert len(train.dataset) == 90 and len(val.dataset) == 10 and len(train) == 11 and len(val) == 1
+    vb = next(iter(val))
+    first_val = data.__class__(100, 16, seed=5, train_ratio=0.0)  # everything is validation: index 90 == val item 0
+    first_val.is_training(False)
+    assert torch.equal(vb["transformed_image1"][0], first_val[90]["transformed_image1"])
+    assert vb["angle_1"].dtype == torch.float64 and vb["jitter_x_1"].dtype == torch.int64
+    # the reference's default ratio (training_config.json: 0.9999999999) leaves no validation batch
+    _, val = get_train_val_split(SyntheticTwoViewDataset(256, 16, train_ratio=0.9999999999), batch_size=8,
+                                 num_workers=0, drop_last=True)
+    assert len(val) == 0
