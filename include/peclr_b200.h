@@ -47,11 +47,12 @@ int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N,
 /* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x) */
 int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, void* stream);
-/* 7x7/stride 2/pad 3 stem (features.0).  xpad = [N][H+6][W+16][4] bf16 from peclr_stem_input,
- * wpack = [64][7][16*4] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
+/* 7x7/stride 2/pad 3 stem (features.0), computed as a 4x4/stride 1 convolution over 2x2 pixel blocks.
+ * xpad = [N][H/2+3][W/2+4][16] bf16 from peclr_stem_input (space-to-depth, zero padded),
+ * wpack = [64][4][4*16] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
 int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
                      float* stat_sumsq, void* stream);
-/* dwpack[64][7][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
+/* dwpack[64][4][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
 int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream);
 
 /* ---- HBM-bound trunk kernels (csrc/bn_act.cu) --------------------------------------------------------
@@ -90,7 +91,8 @@ int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const
                         void* stream);
 int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
 int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream);
-/* cat(transformed_image1, transformed_image2) (hybrid2_model.py:30-32), fp32 NCHW -> padded bf16 NHWC4 */
+/* cat(transformed_image1, transformed_image2) (hybrid2_model.py:30-32), fp32 NCHW -> zero-padded bf16
+ * space-to-depth batch [2B][H/2+3][W/2+4][16] (channel = dy*6 + dx*3 + c of the 2x2 block; 12..15 zero) */
 int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream);
 
 /* ---- projection head, fp32 (csrc/head.cu); replaces SimCLR.get_projection_head modules

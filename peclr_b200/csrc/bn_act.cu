@@ -1,6 +1,6 @@
 // HBM-bound elementwise / reduction kernels of the trunk: training-mode BatchNorm apply (+ residual,
 // + ReLU), BatchNorm backward (reduce + apply), stem max-pool (fused with BN + ReLU) forward/backward,
-// global average pool, and the NCHW fp32 -> padded NHWC4 bf16 input transform.
+// global average pool, and the NCHW fp32 -> padded space-to-depth bf16 input transform.
 //
 // All activation tensors are [M = N*H*W][C] bf16 with C contiguous; every thread owns 8 consecutive
 // channels (one 16-byte vector), keeps the per-channel BatchNorm coefficients in registers and walks
@@ -539,27 +539,42 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
   }
 }
 
-// ---- input transform: two fp32 NCHW view batches -> one zero-padded bf16 NHWC4 batch -----------------
-// out [2B][H + 6][W + 16][4], image pixel (h, w) at (h + 3, w + 3); channel 3 and the border are zero.
+// ---- input transform: two fp32 NCHW view batches -> one zero-padded, space-to-depth bf16 batch -------------
+// out [2B][H/2 + 3][W/2 + 4][16]: block (Y, X) of 2 x 2 image pixels is stored at (Y + 2, X + 2) with its 12 values
+// in channel order (dy, dx, c) -> dy * 6 + dx * 3 + c; channels 12..15 and the border are zero.  The 7x7 / stride 2
+// stem then is a 4 x 4 / stride 1 convolution over 16-channel pixels (csrc/conv_ops.cu, stem_views).
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
-  const int Hp = H + 6, Wp = W + 16;
+  const int Hs = H / 2 + 3, Ws = W / 2 + 4;
   const size_t cs = (size_t)H * W;
-  // one block iteration = one padded row (n, hp); threads walk the padded pixels (coalesced plane reads)
-  for (int row = blockIdx.x; row < 2 * B * Hp; row += gridDim.x) {
-    const int n = row / Hp, hp = row - n * Hp;
-    const int h = hp - 3;
-    const bool row_ok = h >= 0 && h < H;
-    const float* src = (n < B ? x1 + (size_t)n * 3 * cs : x2 + (size_t)(n - B) * 3 * cs) + (size_t)(row_ok ? h : 0) * W;
-    uint2* dst = reinterpret_cast<uint2*>(out) + (size_t)row * Wp;
-    for (int wp = threadIdx.x; wp < Wp; wp += 256) {
-      const int w = wp - 3;
-      uint2 v = make_uint2(0u, 0u);
-      if (row_ok && w >= 0 && w < W) {
-        v.x = pack_bf16x2(src[w], src[cs + w]);
-        v.y = pack_bf16x2(src[2 * cs + w], 0.f);
+  // one block iteration = one padded row (n, yp); threads walk the padded blocks (coalesced float2 plane reads)
+  for (int row = blockIdx.x; row < 2 * B * Hs; row += gridDim.x) {
+    const int n = row / Hs, yp = row - n * Hs;
+    const int y = yp - 2;
+    const bool row_ok = y >= 0 && y < H / 2;
+    const float* src = (n < B ? x1 + (size_t)n * 3 * cs : x2 + (size_t)(n - B) * 3 * cs) +
+                       (size_t)(row_ok ? 2 * y : 0) * W;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)row * Ws * 2;
+    for (int xp = threadIdx.x; xp < Ws; xp += 256) {
+      const int x = xp - 2;
+      uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && x >= 0 && x < W / 2) {
+        float2 v[2][3];  // [dy][c] = pixels (2x, 2x + 1) of image row 2y + dy, plane c
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            v[dy][c] = *reinterpret_cast<const float2*>(src + c * cs + (size_t)dy * W + 2 * x);
+        // channel order: (dy, dx, c)
+        lo.x = pack_bf16x2(v[0][0].x, v[0][1].x);
+        lo.y = pack_bf16x2(v[0][2].x, v[0][0].y);
+        lo.z = pack_bf16x2(v[0][1].y, v[0][2].y);
+        lo.w = pack_bf16x2(v[1][0].x, v[1][1].x);
+        hi.x = pack_bf16x2(v[1][2].x, v[1][0].y);
+        hi.y = pack_bf16x2(v[1][1].y, v[1][2].y);
       }
-      dst[wp] = v;
+      dst[2 * xp] = lo;
+      dst[2 * xp + 1] = hi;
     }
   }
 }
@@ -683,7 +698,8 @@ extern "C" int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int
 }
 
 extern "C" int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream) {
-  stem_input_kernel<<<grid_for((long long)2 * B * (H + 6), 1, 8), 256, 0, (cudaStream_t)stream>>>(
+  if ((H & 1) || (W & 1)) return -1001;
+  stem_input_kernel<<<grid_for((long long)2 * B * (H / 2 + 3), 1, 8), 256, 0, (cudaStream_t)stream>>>(
       x1, x2, (bf16*)out, B, H, W);
   return last_error();
 }

@@ -194,21 +194,19 @@ extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int 
   return conv_wgrad_launch(views, nv, d, taps, num_taps, Cin, Cout, dw, st);
 }
 
-// ---- 7x7 / stride 2 / pad 3 stem on a zero-padded NHWC4 image ------------------------------------
-// xpad: [N][H + 6][W + 16][4] bf16, pixel (h, w) of the image at (h + 3, w + 3), everything else 0.
-// For output (ho, wo) and filter row r the 16-pixel window starting at padded pixel (2ho + r, 2wo) is
-// 64 contiguous bf16: that window is the "channel" dimension of an ordinary K-major GEMM operand.
-// Weights: [64][7][16 * 4] bf16 (taps s >= 7 and channel 3 are zero), K = 448.
-static void stem_views(const void* xpad, int N, int H, int W, View4* views, TapTable* taps) {
-  const int64_t Hp = H + 6, Wp = W + 16;
+// ---- 7x7 / stride 2 / pad 3 stem as a 4x4 / stride 1 convolution on the space-to-depth image ----------------
+// xs: [N][H/2 + 3][W/2 + 4][16] bf16 from peclr_stem_input (2 x 2 pixel blocks as 16-channel pixels, block (Y, X)
+// at (Y + 2, X + 2)).  out(oy, ox) = sum_{ty, tx < 4} w4[ty][tx] . xs(oy + ty, ox + tx): for output (oy, ox) and
+// filter row ty the 4-block window starting at padded block (oy + ty, ox) is 64 contiguous bf16 -- that window is
+// the "channel" dimension of an ordinary K-major GEMM operand (a TMA view whose pixel stride, 16 elements, is
+// smaller than its 64-element rows).  Weights: [64][4][4 * 16] bf16 from peclr_stem_pack, K = 256 (147 non-zero).
+static void stem_views(const void* xs, int N, int H, int W, View4* views, TapTable* taps) {
+  const int64_t Hs = H / 2 + 3, Ws = W / 2 + 4;
   memset(taps, 0, sizeof(*taps));
-  for (int pr = 0; pr < 2; ++pr) {
-    const char* base = static_cast<const char*>(xpad) + (int64_t)pr * Wp * 4 * 2;
-    views[pr] = View4{base, 64, W / 2, Hp / 2, N, 8, 2 * Wp * 4, Hp * Wp * 4};
-  }
-  for (int r = 0; r < 7; ++r) {
-    taps->view[r] = (int8_t)(r & 1);
-    taps->dh[r] = (int8_t)(r >> 1);
+  views[0] = View4{xs, 64, W / 2, Hs, N, 16, Ws * 16, Hs * Ws * 16};
+  for (int r = 0; r < 4; ++r) {
+    taps->view[r] = 0;
+    taps->dh[r] = (int8_t)r;
     taps->dw[r] = 0;
     taps->koff[r] = r * 64;
   }
@@ -221,7 +219,7 @@ extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, in
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_gemm_launch(views, 2, wpack, 7 * 64, 64, d, taps, 7, 1, stat_sum, stat_sumsq, 0,
+  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0,
                           static_cast<cudaStream_t>(stream));
 }
 
@@ -231,5 +229,5 @@ extern "C" int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack,
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{dy, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_wgrad_launch(views, 2, d, taps, 7, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
+  return conv_wgrad_launch(views, 1, d, taps, 4, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
 }

@@ -10,7 +10,8 @@
 //       B tile  = BN output channels x 64, K-major.   D = 128 x BN fp32 accumulator in TMEM.
 //       Strided convolutions read/write parity sub-lattices of the image (plain tiled TMA views with
 //       doubled strides), so one kernel covers 1x1, 3x3, stride 1 and 2, fprop and dgrad, and the
-//       7x7 stem (whose "channels" are 16-pixel x 4-channel windows of a padded NHWC4 image).
+//       7x7 stem (a 4x4 / stride 1 convolution on the space-to-depth image, whose "channels" are 4-block x
+//       16-channel windows of it).
 //       Epilogue: TMEM -> registers -> bf16 -> swizzled smem -> TMA store (or TMA reduce-add for
 //       gradient accumulation), plus per-channel sum / sum-of-squares of the stored values for the
 //       following training-mode BatchNorm.
@@ -374,7 +375,7 @@ struct WgradParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __maxnreg__(80) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
@@ -512,10 +513,11 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + chunk * 32, r);
         tmem_ld_wait();
         if (ci < p.cin) {
+          float* o = out + static_cast<int64_t>(nt * BN + chunk * 32) * p.ld_co;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int co = nt * BN + chunk * 32 + j;
-            red_add_f32(out + co * p.ld_co, __uint_as_float(r[j]));
+            red_add_f32(o, __uint_as_float(r[j]));
+            o += p.ld_co;
           }
         }
       }

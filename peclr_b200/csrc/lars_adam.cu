@@ -123,20 +123,28 @@ __global__ void __launch_bounds__(256) weight_transpose_kernel(const float* __re
   }
 }
 
-// stem weights: master [64][7][7][3] fp32 (channels-last view of (64,3,7,7)) -> [64][7][16][4] bf16, zero padded
+// stem weights: master [64][7][7][3] fp32 (channels-last view of (64,3,7,7)) -> [64][4][4 * 16] bf16 for the
+// space-to-depth form of the stem (4 x 4 taps over 16-channel 2 x 2 pixel blocks): element (co, ty, tx, dy, dx, c)
+// = w[co][c][2 ty + dy - 1][2 tx + dx - 1], zero where that index is -1 and in the 4 padding channels.
 __global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 64 * 7 * 64) return;
-  const int c = i & 3, s = (i >> 2) & 15, r = (i >> 6) % 7, co = i / (7 * 64);
-  const float v = (s < 7 && c < 3) ? w[((co * 7 + r) * 7 + s) * 3 + c] : 0.f;
+  if (i >= 64 * 4 * 64) return;
+  const int ch = i & 15, tx = (i >> 4) & 3, ty = (i >> 6) & 3, co = i >> 8;
+  float v = 0.f;
+  if (ch < 12) {
+    const int dy = ch / 6, dx = (ch % 6) / 3, c = ch % 3;
+    const int r = 2 * ty + dy - 1, s = 2 * tx + dx - 1;
+    if (r >= 0 && s >= 0) v = w[((co * 7 + r) * 7 + s) * 3 + c];
+  }
   out[i] = __float2bfloat16_rn(v);
 }
-// stem weight gradient: packed fp32 [64][7][64] -> += master-layout [64][7][7][3]
+// stem weight gradient: packed fp32 [64][4][64] -> += master-layout [64][7][7][3]
 __global__ void stem_unpack_grad_kernel(const float* __restrict__ gp, float* g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 7 * 7 * 3) return;
   const int c = i % 3, s = (i / 3) % 7, r = (i / 21) % 7, co = i / 147;
-  g[i] += gp[(co * 7 + r) * 64 + s * 4 + c];
+  const int ty = (r + 1) >> 1, dy = (r + 1) & 1, tx = (s + 1) >> 1, dx = (s + 1) & 1;
+  g[i] += gp[(co * 4 + ty) * 64 + tx * 16 + dy * 6 + dx * 3 + c];
 }
 
 }  // namespace peclr
@@ -192,7 +200,7 @@ extern "C" int peclr_weight_transpose(const float* src_flat, void* dst_bf16, con
 }
 
 extern "C" int peclr_stem_pack(const float* w, void* wpack, void* stream) {
-  stem_pack_kernel<<<(64 * 7 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wpack);
+  stem_pack_kernel<<<(64 * 4 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wpack);
   return opt_last_error();
 }
 

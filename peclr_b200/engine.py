@@ -153,7 +153,7 @@ class StepEngine:
         if self.w_bf16 is None:
             self.w_bf16 = torch.empty(self.total, dtype=bf16, device=dev)
             self.wt_bf16 = torch.empty(self.t_total, dtype=bf16, device=dev)
-            self.w_stem = torch.empty((64, 7, 64), dtype=bf16, device=dev)
+            self.w_stem = torch.empty((64, 4, 64), dtype=bf16, device=dev)
             self._t_table = ops.build_transpose_table(self._t_entries, dev)
         _lib.call("peclr_cast_bf16", self.flat, self.w_bf16, self.total, ops._s())
         self.refresh_derived_weights()
@@ -355,7 +355,11 @@ class StepEngine:
         side, keep = self._side, []
         overlap = self.overlap_wgrad
 
+        skip_wgrad = os.environ.get("PECLR_DEBUG_SKIP_WGRAD", "0") == "1"  # timing experiments only (wrong grads)
+
         def wgrad(fn, *alive):
+            if skip_wgrad:
+                return
             if not overlap:
                 return fn()
             keep.extend(alive)

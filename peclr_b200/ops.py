@@ -68,23 +68,24 @@ def conv2d_wgrad(x, dy, k, stride, dw=None):
 
 
 def stem_input(img1, img2, out=None):
-    """two fp32 NCHW batches -> zero-padded bf16 [2B, H+6, W+16, 4]."""
+    """two fp32 NCHW batches -> zero-padded space-to-depth bf16 [2B, H/2+3, W/2+4, 16] (2x2 pixel blocks as
+    16-channel pixels, block (Y, X) at (Y+2, X+2), channel = dy*6 + dx*3 + c)."""
     _need_cuda(img1, img2)
     b, c, h, w = img1.shape
     assert c == 3 and img2.shape == img1.shape and img1.dtype == torch.float32
     if out is None:
-        out = torch.empty((2 * b, h + 6, w + 16, 4), dtype=bf16, device=img1.device)
+        out = torch.empty((2 * b, h // 2 + 3, w // 2 + 4, 16), dtype=bf16, device=img1.device)
     _lib.call("peclr_stem_input", img1, img2, out, b, h, w, _s())
     return out
 
 
 def stem_pack(w_master, out=None):
-    """(64,3,7,7) fp32 channels_last master -> [64,7,64] bf16 packed stem weights."""
+    """(64,3,7,7) fp32 channels_last master -> [64,4,64] bf16 packed stem weights (4x4 taps x 16 channels)."""
     assert w_master.shape == (64, 3, 7, 7)
     flat = w_master.permute(0, 2, 3, 1)
     assert flat.is_contiguous(), "stem weight must be stored channels_last"
     if out is None:
-        out = torch.empty((64, 7, 64), dtype=bf16, device=w_master.device)
+        out = torch.empty((64, 4, 64), dtype=bf16, device=w_master.device)
     _lib.call("peclr_stem_pack", flat, out, _s())
     return out
 
@@ -102,7 +103,7 @@ def stem_fprop(xpad, wpack, h, w, want_stats=False, out=None, stats=None):
 def stem_wgrad(xpad, dy, h, w, dwpack=None):
     n = xpad.shape[0]
     if dwpack is None:
-        dwpack = torch.zeros((64, 7, 64), dtype=torch.float32, device=xpad.device)
+        dwpack = torch.zeros((64, 4, 64), dtype=torch.float32, device=xpad.device)
     _lib.call("peclr_stem_wgrad", xpad, dy, dwpack, n, h, w, _s())
     return dwpack
 

@@ -120,8 +120,14 @@ def test_stem(ops, n, hw):
     w = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).contiguous(memory_format=torch.channels_last)
     xpad = ops.stem_input(img1, img2)
     x = torch.cat([img1, img2]).bfloat16()
-    assert torch.equal(xpad[:, 3:3 + hw, 3:3 + hw, :3], nhwc(x))
-    assert float(xpad[:, :3].abs().sum()) == 0 and float(xpad[..., 3].abs().sum()) == 0
+    # space-to-depth layout: 2x2 pixel block (Y, X) at (Y + 2, X + 2), channel = dy * 6 + dx * 3 + c, rest zero
+    h2 = hw // 2
+    assert xpad.shape == (2 * b, h2 + 3, h2 + 4, 16)
+    blocks = nhwc(x).reshape(2 * b, h2, 2, h2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(2 * b, h2, h2, 12)
+    assert torch.equal(xpad[:, 2:2 + h2, 2:2 + h2, :12], blocks)
+    border = xpad.clone()
+    border[:, 2:2 + h2, 2:2 + h2, :12] = 0
+    assert float(border.abs().sum()) == 0
     wpack = ops.stem_pack(w)
     ref = F.conv2d(x.float(), w.bfloat16().float(), stride=2, padding=3)
     y, stats = ops.stem_fprop(xpad, wpack, hw, hw, want_stats=True)
