@@ -7,7 +7,8 @@ import os
 from ctypes import c_double, c_float, c_int, c_longlong, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpeclr_b200.so")
+# PECLR_B200_LIB: load another build of the same ABI (A/B timing of kernel changes); never a fallback
+LIB_PATH = os.environ.get("PECLR_B200_LIB") or os.path.join(_HERE, "libpeclr_b200.so")
 
 P = c_void_p
 I = c_int

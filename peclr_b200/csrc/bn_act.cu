@@ -341,6 +341,21 @@ static void launch_bn_bwd(const BnBwdArgs& a, int grid, cudaStream_t st) {
 // ---- stem: a = maxpool3x3/s2/p1(relu(bn(y))), y [N][H][W][64] -> a [N][H/2][W/2][64] ----------------
 // also records, per output element, which of the 9 window positions won (first maximum in scan order, as
 // ATen does) so the backward pass is a cheap gather.
+//
+// Both kernels are written for a low instruction count (they were issue-bound, not HBM-bound, as per-channel fp32
+// code): relu(bn(.)) is monotone in y, increasing or decreasing with the sign of gamma*invstd, so the window
+// maximum and its position are found on the RAW bf16 values (sign bit flipped for negative scales) with packed
+// bf16x2 max / compare-mask instructions; BatchNorm + ReLU are applied once, to the winner.  (Where several window
+// values map to the same activation -- all clamped to 0 -- the recorded position may differ from ATen's, but no
+// gradient flows there: the backward pass masks with relu'.  gamma == 0 exactly is the one degenerate case.)
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+
 __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y,
                                                                 const float* sum, const float* sumsq,
                                                                 const float* gamma, const float* beta,
@@ -362,43 +377,66 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
   }
   if (blockIdx.x == 0 && roff == 0)
     bn_bookkeeping(mean, invstd, c0, M, eps, momentum, mean_out, invstd_out, running_mean, running_var);
+  uint32_t flip[4];  // sign-bit flips that make "larger raw value" mean "larger activation"
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    flip[j] = (scale[2 * j] < 0.f ? 0x00008000u : 0u) | (scale[2 * j + 1] < 0.f ? 0x80000000u : 0u);
+  const uint32_t kNegInf = 0xFF80FF80u;
   const int Ho = H / 2, Wo = W / 2;
   // one block iteration = one output row (n, ho); 32 pixel lanes x 8 channel groups walk it (no div/mod inside)
   for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
     const int n = row / Ho, ho = row - n * Ho;
-    const __nv_bfloat16* img = y + (size_t)n * H * W * C + c0;
+    const bool top = ho == 0;  // input row 2ho - 1 is padding (2ho + 1 <= H - 1 always: H is even)
+    const __nv_bfloat16* img = y + ((size_t)n * H + (top ? 0 : 2 * ho - 1)) * W * C + c0;
+    const size_t rstep1 = top ? 0 : (size_t)W * C;  // rows 0 and 1 of the window coincide (clamped) on the top edge
 #pragma unroll 2
     for (int wo = roff; wo < Wo; wo += 32) {
+      const bool left = wo == 0;
+      const __nv_bfloat16* p0 = img + (size_t)(left ? 0 : 2 * wo - 1) * C;
+      const size_t cstep1 = left ? 0 : (size_t)C;
       bf16x8 win[9];
-      bool ok[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const int h = 2 * ho + k / 3 - 1, w = 2 * wo + k % 3 - 1;
-        ok[k] = h >= 0 && h < H && w >= 0 && w < W;
-        if (ok[k]) win[k] = ld8_cached(img + ((size_t)h * W + w) * C);
+      for (int r = 0; r < 3; ++r) {
+        const __nv_bfloat16* pr = p0 + (r == 0 ? 0 : rstep1 + (size_t)(r - 1) * W * C);
+        win[r * 3 + 0] = ld8_cached(pr);
+        win[r * 3 + 1] = ld8_cached(pr + cstep1);
+        win[r * 3 + 2] = ld8_cached(pr + cstep1 + C);
       }
-      float best[8];
-      uint32_t bidx[8];
+      uint32_t best[4], bidx[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) best[i] = -1.f, bidx[i] = 0;  // relu output >= 0 > -1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t t[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        if (!ok[k]) continue;
-        float v[8];
-        unpack8(win[k], v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float act = fmaxf(fmaf(v[i], scale[i], shift[i]), 0.f);
-          if (act > best[i]) best[i] = act, bidx[i] = k;
+        for (int k = 0; k < 9; ++k) {
+          t[k] = win[k].v[j] ^ flip[j];
+          if ((k < 3 && top) || (k % 3 == 0 && left)) t[k] = kNegInf;  // padding never wins (the centre is valid)
         }
+        uint32_t m = t[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) m = bf16x2_max(m, t[k]);
+        uint32_t id = 0x00080008u;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {  // the first position holding the maximum wins
+          const uint32_t eq = bf16x2_eq_mask(t[k], m);
+          id = (id & ~eq) | ((uint32_t)k * 0x00010001u & eq);
+        }
+        best[j] = m ^ flip[j];
+        bidx[j] = id;
       }
-      const size_t o = ((size_t)row * Wo + wo) * C + c0;
-      st8(out + o, pack8(best));
+      bf16x8 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = fmaxf(fmaf(bf16_lo(best[j]), scale[2 * j], shift[2 * j]), 0.f);
+        const float a1 = fmaxf(fmaf(bf16_hi(best[j]), scale[2 * j + 1], shift[2 * j + 1]), 0.f);
+        o.v[j] = pack_bf16x2(a0, a1);
+      }
+      const size_t oo = ((size_t)row * Wo + wo) * C + c0;
+      st8(out + oo, o);
       if (idx_out) {
-        uint2 packed;
-        packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
-        packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
-        *reinterpret_cast<uint2*>(idx_out + o) = packed;
+        uint2 packed;  // bytes 0 and 2 of each 16-bit-lane word
+        packed.x = __byte_perm(bidx[0], bidx[1], 0x6420);
+        packed.y = __byte_perm(bidx[2], bidx[3], 0x6420);
+        *reinterpret_cast<uint2*>(idx_out + oo) = packed;
       }
     }
   }
@@ -406,6 +444,22 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
 
 // backward of the above up to (and excluding) the BN-backward apply: g[pixel] = relu'(.) * sum of dpool over the
 // (at most 4) windows whose recorded winner is this pixel; also accumulates the BN-backward sums.
+// A thread owns 8 channels of the pixel PAIR (2j, 2j + 1) of one input row: the even pixel lies in window column j
+// only (as its middle tap), the odd one in columns j (right tap) and j + 1 (left tap); even rows lie in one window
+// row, odd rows in two (uniform per block iteration).  Winner tests are byte-parallel (__vcmpeq4 on 4 channels).
+__device__ __forceinline__ void pool_bwd_accumulate(const bf16x8& dp, uint2 widx, uint32_t kpos, float (&g)[8]) {
+  const uint32_t want = kpos * 0x01010101u;
+  const uint32_t m0 = __vcmpeq4(widx.x, want), m1 = __vcmpeq4(widx.y, want);  // 0xFF per matching channel byte
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t mb = j < 2 ? m0 : m1;
+    const uint32_t lanes = __byte_perm(mb, 0u, (j & 1) ? 0x3322 : 0x1100);  // byte mask -> 16-bit lane mask
+    const uint32_t v = dp.v[j] & lanes;
+    g[2 * j] += bf16_lo(v);
+    g[2 * j + 1] += bf16_hi(v);
+  }
+}
+
 __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool,
                                                             const uint8_t* __restrict__ idx,
                                                             const __nv_bfloat16* __restrict__ y,
@@ -431,54 +485,49 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
   for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
     const int n = row / H, h = row - n * H;
     const int ho_a = h >> 1, ho_b = (h + 1) >> 1;
-    const bool has_b = (h & 1) && ho_b < Ho;  // odd rows belong to two windows (if the second one exists)
-    const int krow_a = (h - (2 * ho_a - 1)) * 3, krow_b = (h - (2 * ho_b - 1)) * 3;
+    const bool has_b = (h & 1) && ho_b < Ho;  // odd rows belong to two window rows (if the second one exists)
+    const uint32_t krow_a = (uint32_t)(h - (2 * ho_a - 1)) * 3u, krow_b = 0u;  // h is the top tap of window row ho_b
     const size_t pool_a = ((size_t)n * Ho + ho_a) * Wo, pool_b = ((size_t)n * Ho + ho_b) * Wo;
-#pragma unroll 2
-    for (int w = roff; w < W; w += 32) {
-      const size_t o = ((size_t)row * W + w) * C + c0;
-      const bf16x8 yraw = ld8(y + o);
-      const int wo_a = w >> 1, wo_b = (w + 1) >> 1;
-      const bool has_wb = (w & 1) && wo_b < Wo;
-      const int kcol_a = w - (2 * wo_a - 1), kcol_b = w - (2 * wo_b - 1);
-      bf16x8 dp[4];
-      uint2 wi[4];
-      int kpos[4];
-      bool ok[4];
+    for (int j = roff; j < Wo; j += 32) {  // pixel pair (2j, 2j + 1); window columns j and j + 1
+      const size_t o = ((size_t)row * W + 2 * j) * C + c0;
+      const bf16x8 y0 = ld8(y + o), y1 = ld8(y + o + C);
+      const bool has_c = j + 1 < Wo;
+      const size_t pa0 = (pool_a + j) * C + c0, pa1 = pa0 + (has_c ? C : 0);
+      float g0[8], g1[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool hb = q >> 1, wb = q & 1;
-        ok[q] = (!hb || has_b) && (!wb || has_wb);
-        kpos[q] = (hb ? krow_b : krow_a) + (wb ? kcol_b : kcol_a);
-        if (ok[q]) {
-          const size_t po = ((hb ? pool_b : pool_a) + (wb ? wo_b : wo_a)) * C + c0;
-          dp[q] = ld8_cached(dpool + po);
-          wi[q] = *reinterpret_cast<const uint2*>(idx + po);
-        }
+      for (int i = 0; i < 8; ++i) g0[i] = g1[i] = 0.f;
+      {
+        const bf16x8 dpa = ld8_cached(dpool + pa0), dpc = ld8_cached(dpool + pa1);
+        const uint2 ia = *reinterpret_cast<const uint2*>(idx + pa0), ic = *reinterpret_cast<const uint2*>(idx + pa1);
+        pool_bwd_accumulate(dpa, ia, krow_a + 1u, g0);                    // even pixel: middle tap of column j
+        pool_bwd_accumulate(dpa, ia, krow_a + 2u, g1);                    // odd pixel: right tap of column j
+        pool_bwd_accumulate(dpc, ic, has_c ? krow_a : 0xFFu, g1);         // odd pixel: left tap of column j + 1
       }
-      float yv[8], g[8];
-      unpack8(yraw, yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (!ok[q]) continue;
-        float dv[8];
-        unpack8(dp[q], dv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t word = i < 4 ? wi[q].x : wi[q].y;
-          const int win = (word >> (8 * (i & 3))) & 0xFF;
-          g[i] += win == kpos[q] ? dv[i] : 0.f;
-        }
+      if (has_b) {
+        const size_t pb0 = (pool_b + j) * C + c0, pb1 = pb0 + (has_c ? C : 0);
+        const bf16x8 dpa = ld8_cached(dpool + pb0), dpc = ld8_cached(dpool + pb1);
+        const uint2 ia = *reinterpret_cast<const uint2*>(idx + pb0), ic = *reinterpret_cast<const uint2*>(idx + pb1);
+        pool_bwd_accumulate(dpa, ia, krow_b + 1u, g0);
+        pool_bwd_accumulate(dpa, ia, krow_b + 2u, g1);
+        pool_bwd_accumulate(dpc, ic, has_c ? krow_b : 0xFFu, g1);
       }
+      float yv[8];
+      unpack8(y0, yv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        g[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g[i] : 0.f;
-        s[i] += g[i];
-        d[i] = fmaf(g[i], yv[i], d[i]);
+        g0[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g0[i] : 0.f;
+        s[i] += g0[i];
+        d[i] = fmaf(g0[i], yv[i], d[i]);
       }
-      st8(g_out + o, pack8(g));
+      st8(g_out + o, pack8(g0));
+      unpack8(y1, yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g1[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g1[i] : 0.f;
+        s[i] += g1[i];
+        d[i] = fmaf(g1[i], yv[i], d[i]);
+      }
+      st8(g_out + o + C, pack8(g1));
     }
   }
 #pragma unroll

@@ -9,10 +9,12 @@
 namespace peclr {
 
 // C[m, n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]);  32x32 tile, 256 threads, 2x2 each.
+// The GEMMs of the head are tiny (M = 2B rows): blockIdx.z splits K so that a launch fills the machine; with more
+// than one split the partial sums are added atomically into C (zeroed by the host unless it accumulates).
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                             float* C, const float* __restrict__ bias, int M, int N,
                                                             int K, long long sam, long long sak, long long sbk,
-                                                            long long sbn, long long ldc, int accumulate) {
+                                                            long long sbn, long long ldc, int accumulate, int k_per) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -21,7 +23,9 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   // loader mapping: pick the fast index along whichever stride is 1
   const bool a_kfast = sak == 1;
   const bool b_nfast = sbn == 1;
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  const int k_begin = blockIdx.z * k_per;
+  K = min(K, k_begin + k_per);
+  for (int k0 = k_begin; k0 < K; k0 += 32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = threadIdx.x + i * 256;
@@ -55,9 +59,10 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     for (int j = 0; j < 2; ++j) {
       const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2 + j;
       if (gm < M && gn < N) {
-        float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+        float v = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[gn] : 0.f);
         float* c = C + (long long)gm * ldc + gn;
-        *c = accumulate ? *c + v : v;
+        if (gridDim.z > 1) atomicAdd(c, v);
+        else *c = accumulate ? *c + v : v;
       }
     }
 }
@@ -188,9 +193,21 @@ static int head_last_error() {
 extern "C" int peclr_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
                            long long sam, long long sak, long long sbk, long long sbn, long long ldc, int accumulate,
                            void* stream) {
+  if (M < 1 || N < 1 || K < 1) return -1001;
   dim3 grid((N + 31) / 32, (M + 31) / 32);
+  // split K until there are about two blocks per SM (at least 64 of K per split, whole 32-wide k steps)
+  int splits = (2 * 148 + (int)(grid.x * grid.y) - 1) / (int)(grid.x * grid.y);
+  if (splits > K / 64) splits = K / 64;
+  if (splits < 1 || ldc != N) splits = 1;
+  int k_per = ((K + splits - 1) / splits + 31) / 32 * 32;
+  splits = (K + k_per - 1) / k_per;
+  grid.z = splits;
+  if (splits > 1 && !accumulate) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return -(int)e;
+  }
   sgemm_strided_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, M, N, K, sam, sak, sbk, sbn, ldc,
-                                                                accumulate);
+                                                                accumulate, k_per);
   return head_last_error();
 }
 

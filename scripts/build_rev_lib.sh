@@ -1,0 +1,21 @@
+#!/bin/bash
+# usage: scripts/build_rev_lib.sh <git-rev>   -> peclr_b200/libpeclr_b200_old.so built from that revision's csrc/
+# (A/B timing on one GPU box: PECLR_B200_LIB=$PWD/peclr_b200/libpeclr_b200_old.so python bench.py ...)
+set -e
+rev=${1:-HEAD}
+root=$(cd "$(dirname "$0")/.." && pwd)
+tmp=$(mktemp -d)
+mkdir -p "$tmp/peclr_b200/csrc" "$tmp/include"
+for f in $(git -C "$root" ls-tree --name-only "$rev" peclr_b200/csrc/); do git -C "$root" show "$rev:$f" > "$tmp/$f"; done
+git -C "$root" show "$rev:include/peclr_b200.h" > "$tmp/include/peclr_b200.h"
+objs=""
+for src in "$tmp"/peclr_b200/csrc/*.cu; do
+  fast="--use_fast_math"
+  case "$(basename "$src")" in ntxent.cu|equiv_ops.cu|lars_adam.cu|head.cu|bn_act.cu) fast="";; esac
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $fast -c "$src" -o "${src%.cu}.o" &
+  objs="$objs ${src%.cu}.o"
+done
+wait
+nvcc -shared -o "$root/peclr_b200/libpeclr_b200_old.so" $objs -gencode arch=compute_100a,code=sm_100a -cudart static
+rm -rf "$tmp"
+echo "built $root/peclr_b200/libpeclr_b200_old.so from $rev"

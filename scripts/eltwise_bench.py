@@ -53,5 +53,37 @@ def main():
             m, c, t1, 2 * nb / t1 * 1e3, t2, 3 * nb / t2 * 1e3, t3, 5 * nb / t3 * 1e3, t4, 8 * nb / t4 * 1e3))
 
 
+
+
+def stem_main():
+    """Stem pooling kernels at full size (2B = 256, 112 x 112 x 64 conv output): ms and algorithmic GB/s."""
+    n, hw = 256, 112
+    y = torch.randn(n, hw, hw, 64, device="cuda").bfloat16()
+    gamma, beta = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.3
+    yf = y.float().reshape(-1, 64)
+    stats = torch.stack([yf.sum(0), (yf * yf).sum(0)])
+    out, saved, idx = ops.stem_bn_relu_pool(y, stats, gamma, beta)
+    dpool = torch.randn_like(out)
+    dg, db = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
+    scratch = torch.empty(128, device="cuda")
+    g_buf = torch.empty_like(y)
+    t_f = timeit(lambda: ops.stem_bn_relu_pool(y, stats, gamma, beta, out=out, saved=saved))
+    t_b = timeit(lambda: _lib_call_pool_bwd(dpool, idx, y, saved, gamma, beta, g_buf, scratch))
+    ye, oe = y.numel(), out.numel()
+    print("stem_bn_relu_pool  %.3f ms  %6.0f GB/s" % (t_f, (2 * ye + 3 * oe) / t_f / 1e6))
+    print("stem_pool_bwd      %.3f ms  %6.0f GB/s" % (t_b, (4 * ye + 3 * oe) / t_b / 1e6))
+
+
+def _lib_call_pool_bwd(dpool, idx, y, saved, gamma, beta, g_buf, scratch):
+    from peclr_b200 import _lib
+
+    n, h, w, _ = y.shape
+    _lib.call("peclr_stem_pool_bwd", dpool, idx, y, saved[0], saved[1], gamma, beta, g_buf, scratch, n, h, w,
+              _lib.stream_ptr())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "stem":
+        stem_main()
+    else:
+        main()
