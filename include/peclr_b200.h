@@ -21,6 +21,10 @@ extern "C" {
 #endif
 
 int peclr_abi_version(void);
+/* R = number of accumulator sets in a BN-backward "scratch" buffer: where a scratch is documented as [2C] it is
+ * float[R][2C]; block b adds into set b % R and the consumer adds the sets in order (fewer atomics serialised on
+ * one address). */
+int peclr_stat_replicas(void);
 
 /* ---- ResNet trunk convolutions: tcgen05/TMEM implicit GEMM fed by TMA (csrc/conv_tc.cu) ------------
  * Replace nn.Conv2d forward/backward inside ResNetModel.features
@@ -30,9 +34,11 @@ int peclr_abi_version(void);
 
 /* y[N,H/s,W/s,Cout] = conv(x[N,H,W,Cin], w[Cout][k*k][Cin]); if stat_sum != NULL also accumulates
  * per-output-channel sum and sum of squares of the stored bf16 y (training-mode BatchNorm statistics;
- * the two float[Cout] buffers must be zeroed by the caller). */
+ * the two double[Cout] buffers must be zeroed by the caller).  The forward statistics are fp64 accumulators: each
+ * CTA adds a partial computed in a fixed order, so the fp32 mean / variance derived from the totals do not depend on
+ * the order of arrival and the forward pass (hence the loss) is reproducible from run to run. */
 int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
-                       int stride, float* stat_sum, float* stat_sumsq, void* stream);
+                       int stride, double* stat_sum, double* stat_sumsq, void* stream);
 /* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,H/s,W/s,Cout], wt[Cin][k*k][Cout]); wt is the transposed
  * weight copy produced by peclr_weight_transpose.  accumulate != 0 adds into dx (TMA reduce-add). */
 int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
@@ -50,8 +56,8 @@ int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, i
 /* 7x7/stride 2/pad 3 stem (features.0), computed as a 4x4/stride 1 convolution over 2x2 pixel blocks.
  * xpad = [N][H/2+3][W/2+4][16] bf16 from peclr_stem_input (space-to-depth, zero padded),
  * wpack = [64][4][4*16] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
-int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
-                     float* stat_sumsq, void* stream);
+int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, double* stat_sum,
+                     double* stat_sumsq, void* stream);
 /* dwpack[64][4][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
 int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream);
 
@@ -63,8 +69,8 @@ int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int
  * finished activation (rsum == NULL) or a raw conv output with its own BatchNorm (downsample branch).
  * Saves mean / invstd for backward and updates running stats (momentum, unbiased var) as PyTorch does.
  * mask_out (optional, uint8 [M][C/8]) receives the ReLU mask as bits for peclr_bn_bwd_* mask_mode 3. */
-int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
-                   const void* res, const float* rsum, const float* rsumsq, const float* rgamma, const float* rbeta,
+int peclr_bn_apply(const void* y, const double* sum, const double* sumsq, const float* gamma, const float* beta,
+                   const void* res, const double* rsum, const double* rsumsq, const float* rgamma, const float* rbeta,
                    void* out, void* mask_out, float* mean_out, float* invstd_out, float* running_mean,
                    float* running_var,
                    float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
@@ -81,7 +87,7 @@ int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const 
                        void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream);
 /* out[N,H/2,W/2,64] = maxpool3x3s2p1(relu(bn(y[N,H,W,64])))   (features.1-3); idx_out (uint8, same shape as
  * out, may be NULL) records the winning window position 0..8 for the backward pass */
-int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
+int peclr_stem_bn_relu_pool(const void* y, const double* sum, const double* sumsq, const float* gamma,
                             const float* beta, void* out, void* idx_out, float* mean_out, float* invstd_out,
                             float* running_mean, float* running_var, int N, int H, int W, float eps, float momentum,
                             void* stream);

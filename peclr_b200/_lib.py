@@ -18,6 +18,7 @@ F = c_float
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "peclr_abi_version": [],
+    "peclr_stat_replicas": [],
     "peclr_conv2d_fprop": [P, P, P, I, I, I, I, I, I, I, P, P, P],
     "peclr_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, P],
     "peclr_conv2d_dgrad_bnreduce": [P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
@@ -52,7 +53,7 @@ SIGNATURES = {
     "peclr_stem_unpack_grad": [P, P, P],
 }
 _RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong}
-_NO_CHECK = {"peclr_abi_version", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems"}
+_NO_CHECK = {"peclr_abi_version", "peclr_stat_replicas", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems"}
 
 _ERRORS = {-1001: "bad argument", -1002: "CUDA driver entry point unavailable", -1003: "TMA tensor-map encoding failed"}
 

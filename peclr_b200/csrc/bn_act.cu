@@ -10,6 +10,7 @@
 // Replaces ATen/cuDNN BatchNorm2d(train) + ReLU + residual add + MaxPool2d + AdaptiveAvgPool2d of the
 // reference trunk (src/models/resnet_model.py:16-26; torchvision ResNet.forward).
 #include "../../include/peclr_b200.h"
+#include "conv_tc.h"
 #include "ptx.cuh"
 
 namespace peclr {
@@ -45,12 +46,22 @@ __device__ __forceinline__ bf16x8 ld8_cached(const __nv_bfloat16* p) { return *r
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
 // mean / inverse std of 8 channels from the sums the convolution epilogue accumulated
-__device__ __forceinline__ void bn_coeffs(const float* sum, const float* sumsq, int c0, float inv_m, float eps,
+// BN-backward scratch: [kStatReplicas][2C] fp32 accumulator sets, added in order
+__device__ __forceinline__ float stat_total(const float* base, long long stride, int idx) {
+  float t = base[idx];
+#pragma unroll
+  for (int r = 1; r < kStatReplicas; ++r) t += base[r * stride + idx];
+  return t;
+}
+// sum / sumsq: double[C] totals of the conv epilogue.  They are rounded to fp32 at once: fp64 arithmetic is slow on
+// this part (a per-thread fp64 mean / variance cost ~8 us per launch), the fp64 accumulation is only there to make
+// the totals independent of the order in which the CTAs' partial sums arrived.
+__device__ __forceinline__ void bn_coeffs(const double* sum, const double* sumsq, int c0, float inv_m, float eps,
                                           float (&mean)[8], float (&invstd)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float m = sum[c0 + i] * inv_m;
-    const float var = fmaxf(sumsq[c0 + i] * inv_m - m * m, 0.f);
+    const float m = (float)sum[c0 + i] * inv_m;
+    const float var = fmaxf((float)sumsq[c0 + i] * inv_m - m * m, 0.f);
     mean[i] = m;
     invstd[i] = rsqrtf(var + eps);
   }
@@ -82,9 +93,11 @@ __device__ __forceinline__ RowWalk row_walk(long long M, int rows_per_block, int
 
 struct BnApplyArgs {
   const __nv_bfloat16* y;
-  const float *sum, *sumsq, *gamma, *beta;
+  const double *sum, *sumsq;
+  const float *gamma, *beta;
   const __nv_bfloat16* res;                     // optional second operand of the residual add
-  const float *rsum, *rsumsq, *rgamma, *rbeta;  // if non-null, res is a raw conv output with its own BN
+  const double *rsum, *rsumsq;  // if non-null, res is a raw conv output with its own BN
+  const float *rgamma, *rbeta;
   __nv_bfloat16* out;
   uint8_t* mask_out;  // optional [M][C/8]: bit i of byte (row, channel group) = out[8g + i] > 0
   float *mean_out, *invstd_out, *running_mean, *running_var;
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 struct BnBwdArgs {
   const __nv_bfloat16 *dout, *mask, *y;
   const float *mean, *invstd, *gamma, *beta;
-  float* scratch;          // [2C]: sum g, sum g*y
+  float* scratch;          // [kStatReplicas][2C]: sum g, sum g*y
   __nv_bfloat16 *dy, *g_out;
   float *dgamma, *dbeta;
   long long M;
@@ -226,7 +239,8 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
     }
     s[i] = d[i] = 0.f;
     if (kApply) {
-      const float sg = a.scratch[c0 + i], sgy = a.scratch[a.C + c0 + i];
+      const float sg = stat_total(a.scratch, 2 * a.C, c0 + i);
+      const float sgy = stat_total(a.scratch, 2 * a.C, a.C + c0 + i);
       const float sgx = is * (sgy - mu * sg);
       const float k2 = sg * inv_m, k3 = sgx * inv_m;
       ka[i] = gm * is;
@@ -296,8 +310,9 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        red_add_f32(a.scratch + c0 + i, s[i]);
-        red_add_f32(a.scratch + a.C + c0 + i, d[i]);
+        float* set = a.scratch + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.C;
+        red_add_f32(set + c0 + i, s[i]);
+        red_add_f32(set + a.C + c0 + i, d[i]);
       }
     }
   }
@@ -357,7 +372,7 @@ __device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
 }
 
 __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y,
-                                                                const float* sum, const float* sumsq,
+                                                                const double* sum, const double* sumsq,
                                                                 const float* gamma, const float* beta,
                                                                 __nv_bfloat16* __restrict__ out,
                                                                 uint8_t* __restrict__ idx_out, float* mean_out,
@@ -540,8 +555,9 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      red_add_f32(scratch + c0 + i, s[i]);
-      red_add_f32(scratch + C + c0 + i, d[i]);
+      float* set = scratch + (size_t)(blockIdx.x % kStatReplicas) * 2 * C;
+      red_add_f32(set + c0 + i, s[i]);
+      red_add_f32(set + C + c0 + i, d[i]);
     }
   }
 }
@@ -664,8 +680,8 @@ static bool bad_channels(int C) { return C % 8 || C > 2048 || C < 8 || (256 % (C
 using namespace peclr;
 typedef __nv_bfloat16 bf16;
 
-extern "C" int peclr_bn_apply(const void* y, const float* sum, const float* sumsq, const float* gamma,
-                              const float* beta, const void* res, const float* rsum, const float* rsumsq,
+extern "C" int peclr_bn_apply(const void* y, const double* sum, const double* sumsq, const float* gamma,
+                              const float* beta, const void* res, const double* rsum, const double* rsumsq,
                               const float* rgamma, const float* rbeta, void* out, void* mask_out, float* mean_out,
                               float* invstd_out,
                               float* running_mean, float* running_var, float* rmean_out, float* rinvstd_out,
@@ -688,7 +704,7 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
                                    const float* invstd, const float* gamma, const float* beta, int mask_mode,
                                    float* scratch, long long M, int C, void* stream) {
   if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)C * 4, (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * C * sizeof(float), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
               nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode, elt_contig()};
@@ -709,7 +725,7 @@ extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void
   return last_error();
 }
 
-extern "C" int peclr_stem_bn_relu_pool(const void* y, const float* sum, const float* sumsq, const float* gamma,
+extern "C" int peclr_stem_bn_relu_pool(const void* y, const double* sum, const double* sumsq, const float* gamma,
                                        const float* beta, void* out, void* idx_out, float* mean_out,
                                        float* invstd_out, float* running_mean, float* running_var, int N, int H,
                                        int W, float eps, float momentum, void* stream) {
@@ -724,7 +740,7 @@ extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const voi
                                    const float* invstd, const float* gamma, const float* beta, void* g_out,
                                    float* scratch, int N, int H, int W, void* stream) {
   if ((H & 1) || (W & 1) || !idx) return -1001;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * 64 * 4, (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * 64 * sizeof(float), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   stem_pool_bwd_kernel<<<grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H,

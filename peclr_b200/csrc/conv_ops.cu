@@ -58,8 +58,10 @@ static int input_side(const void* x, int N, int H, int W, int C, int k, int stri
 
 using namespace peclr;
 
+extern "C" int peclr_stat_replicas(void) { return kStatReplicas; }
+
 extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
-                                  int stride, float* stat_sum, float* stat_sumsq, void* stream) {
+                                  int stride, double* stat_sum, double* stat_sumsq, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cin % 64 || Cout % 64) return PECLR_ERR_ARG;
   const int Ho = H / stride, Wo = W / stride;
@@ -70,13 +72,13 @@ extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, 
     memset(&taps, 0, sizeof(taps));
     views[0] = flat_view(x, (int64_t)N * H * W, Cin);
     View4 d = flat_view(y, (int64_t)N * H * W, Cout);
-    return conv_gemm_launch(views, 1, w, Cin, Cout, d, taps, 1, Cin / 64, stat_sum, stat_sumsq, 0, st);
+    return conv_gemm_launch(views, 1, w, Cin, Cout, d, taps, 1, Cin / 64, stat_sum, stat_sumsq, 0, 0, st);
   }
   const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
   if (nv < 0) return nv;
   View4 d = nhwc_view(y, N, Ho, Wo, Cout);
   return conv_gemm_launch(views, nv, w, (int64_t)num_taps * Cin, Cout, d, taps, num_taps, Cin / 64, stat_sum,
-                          stat_sumsq, 0, st);
+                          stat_sumsq, 0, 0, st);
 }
 
 // dgrad, optionally with the BatchNorm-backward reduction of the BN (+ReLU) in front of this convolution fused
@@ -94,7 +96,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
   float* s_sum = bn_y ? scratch : nullptr;
   float* s_sq = bn_y ? scratch + Cin : nullptr;
   if (bn_y) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * (size_t)Cin * 4, st);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * Cin * sizeof(float), st);
     if (e != cudaSuccess) return -(int)e;
   }
   // the y tile of a launch sits at the same offset from bn_y as the output view does from dx
@@ -109,7 +111,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
     if (k == 1) {
       a = flat_view(dy, (int64_t)N * H * W, Cout);
       View4 d = flat_view(dx, (int64_t)N * H * W, Cin);
-      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, s_sum, s_sq, accumulate, st,
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
                               bnr_for(d, &br));
     }
     a = nhwc_view(dy, N, H, W, Cout);
@@ -121,7 +123,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
         taps.koff[t] = t * Cout;
       }
     View4 d = nhwc_view(dx, N, H, W, Cin);
-    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, accumulate, st,
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
                             bnr_for(d, &br));
   }
   if (stride != 2 || (H & 1) || (W & 1)) return PECLR_ERR_ARG;
@@ -134,7 +136,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
       if (e != cudaSuccess) return -(int)e;
     }
     View4 d = parity_view(dx, N, H, W, Cin, 0, 0);
-    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, accumulate, st);
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, 0, accumulate, st);
   }
   // 3x3 stride 2: one launch per parity class of the input pixel; taps r with (ph + 1 - r) even
   for (int ph = 0; ph < 2; ++ph)
@@ -152,7 +154,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
         }
       }
       View4 d = parity_view(dx, N, H, W, Cin, ph, pw);
-      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, s_sum, s_sq, accumulate, st,
+      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
                                 bnr_for(d, &br));
       if (rc) return rc;
     }
@@ -212,14 +214,14 @@ static void stem_views(const void* xs, int N, int H, int W, View4* views, TapTab
   }
 }
 
-extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, float* stat_sum,
-                                float* stat_sumsq, void* stream) {
+extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, double* stat_sum,
+                                double* stat_sumsq, void* stream) {
   if ((H & 1) || (W & 1)) return PECLR_ERR_ARG;
   View4 views[kMaxViews];
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0,
+  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0, 0,
                           static_cast<cudaStream_t>(stream));
 }
 

@@ -45,8 +45,13 @@ struct GemmParams {
   int log_wb, log_wbhb;
   int d_w, d_h, d_n;
   int cout;
-  float* stat_sum;
-  float* stat_sumsq;
+  // per-channel statistics of the stored tile values, accumulated across CTAs.  Forward (BatchNorm sums): fp64
+  // accumulators (see red_add_f64).  Fused BN-backward reduction (stat_f32): fp32 accumulators in kStatReplicas
+  // sets stat_stride elements apart, CTA b adds into set b % kStatReplicas.
+  void* stat_sum;
+  void* stat_sumsq;
+  long long stat_stride;
+  int stat_f32;
   int reduce_add;
   // fused BatchNorm-backward reduction (dgrad feeding an inner BN + ReLU): with y = that BN's input tile,
   // g = D * [fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0]; stat_sum += sum g, stat_sumsq += sum g*y
@@ -342,8 +347,14 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         float s = 0.f, qq = 0.f;
         for (int g = 0; g < p.stat_copies; ++g) s += sStat[g * 2 * p.cout + i], qq += sStat[g * 2 * p.cout + p.cout + i];
         if (s != 0.f || qq != 0.f) {
-          red_add_f32(p.stat_sum + i, s);
-          red_add_f32(p.stat_sumsq + i, qq);
+          if (p.stat_f32) {
+            const long long rep = (long long)(blockIdx.x % kStatReplicas) * p.stat_stride;
+            red_add_f32(static_cast<float*>(p.stat_sum) + rep + i, s);
+            red_add_f32(static_cast<float*>(p.stat_sumsq) + rep + i, qq);
+          } else {
+            red_add_f64(static_cast<double*>(p.stat_sum) + i, (double)s);
+            red_add_f64(static_cast<double*>(p.stat_sumsq) + i, (double)qq);
+          }
         }
       }
     }
@@ -663,8 +674,8 @@ static bool use_cta_pairs() {
 }
 
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
-                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
-                     float* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr) {
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
+                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr) {
   if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
   if (nout % 64 != 0 || ktot % 64 != 0 || d_view.c != nout) return PECLR_ERR_ARG;
   if (stat_sum && nout > 2048) return PECLR_ERR_ARG;
@@ -708,6 +719,8 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.cout = (int)nout;
   p.stat_sum = stat_sum;
   p.stat_sumsq = stat_sumsq;
+  p.stat_stride = stat_stride;
+  p.stat_f32 = bnr != nullptr;  // forward BatchNorm sums are fp64; the fused BN-backward reduction uses fp32 sets
   p.reduce_add = reduce_add;
   const bool stats = stat_sum != nullptr;
   if (pairs) {

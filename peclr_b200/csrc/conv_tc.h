@@ -11,6 +11,13 @@
 
 namespace peclr {
 
+// The BN-backward sums (scratch buffers) are kept as kStatReplicas fp32 accumulator sets: block b adds its partial
+// into set b % kStatReplicas, the consumer adds the sets in order.  Replication divides the number of atomics
+// serialised on one address (the tail of the reduction kernels; measured 4-12 us per launch).  The forward
+// statistics of the conv epilogue are one fp64 set: fp64 makes the totals independent of the order in which the
+// CTAs' partials arrive (the forward pass, hence the loss, is reproducible run to run); the backward sums stay fp32
+// because fp64 arithmetic in the consumers' per-thread prologues is slow on this part (+0.4 ms per step measured).
+constexpr int kStatReplicas = 4;
 constexpr int kMaxViews = 4;
 constexpr int kMaxTaps = 16;
 
@@ -41,8 +48,8 @@ struct BnReduce {
 
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
-                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, float* stat_sum,
-                     float* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr);
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
+                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr);
 
 // dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin)
 int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,

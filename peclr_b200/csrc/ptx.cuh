@@ -248,6 +248,12 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
 }
+// Cross-CTA sums of per-CTA partial statistics are accumulated in fp64: every partial is computed in a fixed order,
+// and an fp64 sum of a few hundred fp32 values is independent of the arrival order to ~1e-16, so the fp32 values
+// derived from it (BatchNorm mean / variance, BN-backward sums) are reproducible from run to run.
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));

@@ -185,7 +185,7 @@ class StepEngine:
         """Training: the conv epilogue's sums.  Eval: sums synthesised from the running statistics."""
         if training:
             return stats
-        mean, var = bn.running_mean, bn.running_var
+        mean, var = bn.running_mean.double(), bn.running_var.double()
         return torch.stack([mean * m, (var + mean * mean) * m])
 
     def forward_trunk(self, img1, img2, training=True):
@@ -199,7 +199,7 @@ class StepEngine:
         convs = [self.stem_conv] + [c for blk in self.blocks for c, _ in blk.convs()] + \
                 [blk.downsample[0] for blk in self.blocks if blk.downsample is not None]
         tot = sum(c.cout for c in convs)
-        stats_all = torch.zeros((2 * tot,), dtype=torch.float32, device=dev)
+        stats_all = torch.zeros((2 * tot,), dtype=torch.float64, device=dev)  # fp64 cross-CTA accumulators
         saved_all = torch.empty((2 * tot,), dtype=torch.float32, device=dev)
         cur = [0]
 
@@ -345,7 +345,7 @@ class StepEngine:
         dev = self.device
         n = ctx["n"]
         da = ops.avgpool_bwd(d_enc, ctx["final_shape"])
-        scratch = torch.empty((4096,), dtype=torch.float32, device=dev)
+        scratch = ops.new_scratch(2048, dev)
         # Weight gradients are off the critical path (they only feed the optimiser): they go to a side stream so
         # the tensor-core-bound wgrad kernels overlap with the HBM-bound BatchNorm / dgrad chain.  Their inputs
         # are kept alive until the streams join (no allocator reuse while the side stream may still read them).

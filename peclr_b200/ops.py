@@ -12,6 +12,29 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+f64 = torch.float64  # the conv epilogue's BatchNorm sums are fp64 accumulators (order independent -> reproducible)
+
+
+def stat_replicas():
+    """R: a BN-backward scratch buffer holds R fp32 accumulator sets (include/peclr_b200.h)."""
+    return _lib.call("peclr_stat_replicas")
+
+
+def new_stats(c, device):
+    """Zeroed [2][C] fp64 buffer for the conv epilogue's per-channel sum / sum of squares."""
+    return torch.zeros((2, c), dtype=f64, device=device)
+
+
+def new_scratch(c, device):
+    """[R][2C] fp32 buffer for the BN-backward sums (zeroed by the kernels that fill it)."""
+    return torch.empty((stat_replicas() * 2 * c,), dtype=torch.float32, device=device)
+
+
+def _sums(t):
+    """Statistic sums as the kernels expect them: fp64 [2][C] (callers may hand in fp32 totals they computed)."""
+    return t if t is None or t.dtype == f64 else t.to(f64)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -22,13 +45,14 @@ def _need_cuda(*ts):
 
 # ------------------------------------------------------------------ convolutions
 def conv2d_fprop(x, w, k, stride, want_stats=False, out=None, stats=None):
-    """x [N,H,W,Cin] bf16, w [Cout,k*k,Cin] bf16 -> y [N,H/s,W/s,Cout] bf16 (+ stats [2,Cout] fp32)."""
+    """x [N,H,W,Cin] bf16, w [Cout,k*k,Cin] bf16 -> y [N,H/s,W/s,Cout] bf16 (+ stats [2,Cout] fp64: per-channel
+    sum and sum of squares of the stored y)."""
     _need_cuda(x, w)
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     y = out if out is not None else torch.empty((n, h // stride, wd // stride, cout), dtype=bf16, device=x.device)
     if want_stats and stats is None:
-        stats = torch.zeros((2, cout), dtype=torch.float32, device=x.device)
+        stats = new_stats(cout, x.device)
     _lib.call("peclr_conv2d_fprop", x, w, y, n, h, wd, cin, cout, k, stride,
               stats[0] if stats is not None else None, stats[1] if stats is not None else None, _s())
     return (y, stats) if want_stats else y
@@ -46,7 +70,8 @@ def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False):
 
 def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta, scratch, out=None):
     """dgrad whose epilogue also accumulates the BatchNorm-backward sums of the BN + ReLU in front of the conv
-    (scratch [2*Cin] fp32: sum g, sum g*y).  Follow with bn_backward(..., scratch=scratch, reduce_done=True)."""
+    (scratch [R][2*Cin] fp32 sets: sum g, sum g*y).  Follow with bn_backward(..., scratch=scratch, reduce_done=True)."""
+    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 2 * in_shape[-1]
     _need_cuda(dy, wt, bn_y)
     n, h, wd, cin = in_shape
     cout = dy.shape[-1]
@@ -94,7 +119,7 @@ def stem_fprop(xpad, wpack, h, w, want_stats=False, out=None, stats=None):
     n = xpad.shape[0]
     y = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=xpad.device)
     if want_stats and stats is None:
-        stats = torch.zeros((2, 64), dtype=torch.float32, device=xpad.device)
+        stats = new_stats(64, xpad.device)
     _lib.call("peclr_stem_fprop", xpad, wpack, y, n, h, w,
               stats[0] if stats is not None else None, stats[1] if stats is not None else None, _s())
     return (y, stats) if want_stats else y
@@ -122,6 +147,7 @@ def bn_apply(y, stats, gamma, beta, relu=True, res=None, res_bn=None, running=No
     if rsaved is None and res_bn is not None:
         rsaved = torch.empty((2, c), dtype=torch.float32, device=dev)
     rstats, rgamma, rbeta, rrunning = res_bn if res_bn is not None else (None, None, None, None)
+    stats, rstats = _sums(stats), _sums(rstats)
     _lib.call(
         "peclr_bn_apply", y, stats[0], stats[1], gamma, beta, res,
         rstats[0] if rstats is not None else None, rstats[1] if rstats is not None else None, rgamma, rbeta,
@@ -142,7 +168,8 @@ def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratc
     # mask: bf16 activation (mode 1) or the uint8 bit mask bn_apply wrote (mode 3)
     mode = (3 if mask.dtype == torch.uint8 else 1) if mask is not None else (2 if beta is not None else 0)
     if scratch is None:
-        scratch = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+        scratch = new_scratch(c, y.device)
+    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 2 * c
     dy = dy if dy is not None else torch.empty_like(y)
     if want_g and g_out is None:
         g_out = torch.empty_like(y)
@@ -158,6 +185,7 @@ def stem_bn_relu_pool(y, stats, gamma, beta, running=None, eps=1e-5, momentum=0.
     """Returns pooled activation, saved (mean, invstd), idx (uint8 winners, or None)."""
     n, h, w, c = y.shape
     assert c == 64
+    stats = _sums(stats)
     out = out if out is not None else torch.empty((n, h // 2, w // 2, 64), dtype=bf16, device=y.device)
     idx = torch.empty((n, h // 2, w // 2, 64), dtype=torch.uint8, device=y.device) if want_idx else None
     if saved is None:
@@ -172,7 +200,8 @@ def stem_pool_bn_backward(dpool, idx, y, saved, gamma, beta, dgamma, dbeta, g_bu
     """Backward through maxpool + relu + stem BN.  Returns dy (grad of the raw stem conv output)."""
     n, h, w, c = y.shape
     if scratch is None:
-        scratch = torch.empty((128,), dtype=torch.float32, device=y.device)
+        scratch = new_scratch(64, y.device)
+    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 128
     g = g_buf if g_buf is not None else torch.empty_like(y)
     _lib.call("peclr_stem_pool_bwd", dpool, idx, y, saved[0], saved[1], gamma, beta, g, scratch, n, h, w, _s())
     # pass 2: plain BN backward apply on the already masked gradient (in place: dy overwrites g)

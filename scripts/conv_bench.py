@@ -79,7 +79,7 @@ def main():
         y = torch.empty(n, ho, ho, cout, device="cuda", dtype=torch.bfloat16)
         dx = torch.empty_like(x)
         dw = torch.zeros(cout, k * k, cin, device="cuda")
-        stats = torch.zeros(2, cout, device="cuda")
+        stats = ops.new_stats(cout, "cuda")
         flops = 2.0 * n * ho * ho * cout * cin * k * k
         t_f = timeit(lambda: ops.conv2d_fprop(x, w, k, s, out=y, stats=stats))
         t_n = timeit(lambda: ops.conv2d_fprop(x, w, k, s, out=y))

@@ -77,7 +77,7 @@ def main():
         yf = y.float().view(m, c)
         saved = torch.stack([yf.mean(0), torch.rsqrt(yf.var(0, unbiased=False) + 1e-5)])
         dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
-        scratch = torch.empty(2 * c, device="cuda")
+        scratch = ops.new_scratch(c, "cuda")
 
         def wg():
             ops.conv2d_wgrad(x, dyc, k, 1, dw=dw)

@@ -44,8 +44,9 @@ def test_conv_adjointness_full_size(shape):
     assert abs(s1 - s2) <= 2e-3 * scale and abs(s1 - s3) <= 2e-3 * scale, (s1, s2, s3, scale)
     # the epilogue statistics are the sums of what was stored
     yf = y.float().reshape(-1, cout)
-    assert torch.allclose(stats[0], yf.sum(0), rtol=2e-3, atol=2e-3 * float(yf.abs().sum(0).max()))
-    assert torch.allclose(stats[1], (yf * yf).sum(0), rtol=2e-3)
+    tot = stats.float()
+    assert torch.allclose(tot[0], yf.sum(0), rtol=2e-3, atol=2e-3 * float(yf.abs().sum(0).max()))
+    assert torch.allclose(tot[1], (yf * yf).sum(0), rtol=2e-3)
     # linearity in the weights: conv(x, 2w) = 2 conv(x, w) exactly (power-of-two scaling commutes with rounding)
     y2 = ops.conv2d_fprop(x, (w.float() * 2).bfloat16(), k, s)
     assert torch.equal(y2.float(), 2 * y.float())

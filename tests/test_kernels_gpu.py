@@ -70,6 +70,8 @@ def test_conv_fprop_and_stats(ops, case):
     assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
     # statistics are those of the stored bf16 tensor
     yf = y.float().reshape(-1, cout)
+    assert stats.dtype == torch.float64 and stats.shape == (2, yf.shape[1])
+    stats = stats.float()
     assert torch.allclose(stats[0], yf.sum(0), rtol=1e-3, atol=1e-2 * yf.abs().sum(0).max().item() / 100)
     assert torch.allclose(stats[1], (yf * yf).sum(0), rtol=1e-3, atol=1e-3)
 
@@ -134,7 +136,7 @@ def test_stem(ops, n, hw):
     torch.cuda.synchronize()
     assert rel_l2(y.permute(0, 3, 1, 2).float(), ref) < 1e-2
     yf = y.float().reshape(-1, 64)
-    assert torch.allclose(stats[0], yf.sum(0), rtol=1e-3, atol=1e-1)
+    assert torch.allclose(stats[0].float(), yf.sum(0), rtol=1e-3, atol=1e-1)
     dy = torch.randn(2 * b, 64, hw // 2, hw // 2, device="cuda", generator=g).bfloat16()
     ref_dw = torch.nn.grad.conv2d_weight(x.float(), w.shape, dy.float(), stride=2, padding=3)
     dwp = ops.stem_wgrad(xpad, nhwc(dy), hw, hw)
@@ -391,12 +393,14 @@ def test_dgrad_with_fused_bn_reduce(ops, case):
     yf = y_prev.float().reshape(-1, cin)
     saved = torch.stack([yf.mean(0), torch.rsqrt(yf.var(0, unbiased=False) + 1e-5)])
     plain = ops.conv2d_dgrad(dy, wt_t, (n, h, w, cin), k, s)
-    scratch = torch.full((2 * cin,), 123.0, device="cuda")
+    reps = ops.stat_replicas()
+    scratch = torch.full((reps * 2 * cin,), 123.0, device="cuda")
     fused = ops.conv2d_dgrad_bnreduce(dy, wt_t, (n, h, w, cin), k, s, y_prev, saved, gamma, beta, scratch)
-    ref = torch.empty(2 * cin, device="cuda")
+    ref = torch.empty(reps * 2 * cin, device="cuda")
     _lib.call("peclr_bn_bwd_reduce", plain, None, y_prev, saved[0], saved[1], gamma, beta, 2, ref, n * h * w, cin,
               _lib.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(fused, plain)
+    ref, scratch = ref.view(reps, -1).sum(0), scratch.view(reps, -1).sum(0)  # the accumulator sets add up
     scale = ref.abs().max().item()
     assert (scratch - ref).abs().max().item() <= 2e-3 * scale, ((scratch - ref).abs().max().item(), scale)
