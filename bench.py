@@ -31,9 +31,12 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-def ncu_traffic():
+def ncu_traffic(args):
     """dram__bytes_read + dram__bytes_write per conv_gemm_kernel launch (average over the launches of one step),
-    from the committed ncu capture (profiles/roofline_r01.json); None if the capture is missing."""
+    from the committed ncu capture (profiles/roofline_r01.json, taken on the default ResNet-50 workload); None for
+    any other workload or if the capture is missing."""
+    if (args.model, args.batch, args.size) != ("50", 128, 224):
+        return None
     try:
         return int(json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))["dram_bytes_per_launch"])
     except Exception:
@@ -60,7 +63,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.03)
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -251,7 +254,7 @@ def run_ours(args):
         f_train = F_TRAIN.get((args.model, args.size))
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM fprop+dgrad)",
                 "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(),
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(args),
                 "peak_source": pk["src"] + " (sustained)",
                 "kernel_ms_per_step": round(times["gemm"], 3),
                 "wgrad_kernel": {"achieved": round(ach_w, 1), "frac": round(ach_w / pk["tf_sustained"], 4),
@@ -344,7 +347,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = pick_sample_batch(args, target_s=2.5)
+    # bounded sample per step so that the whole --steps K --warmup W run stays within ~2 minutes of CPU work
+    b = pick_sample_batch(args, target_s=min(2.5, 120.0 / max(1, args.steps + args.warmup)))
     po, model, opt, sched = _oracle_model(args, b)
     data = po.synthetic_batch(b, args.size, seed=5, structured=False)
     for _ in range(args.warmup):
@@ -373,8 +377,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="50", choices=["18", "34", "50", "101", "152"])
     ap.add_argument("--batch", type=int, default=128)
