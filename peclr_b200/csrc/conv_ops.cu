@@ -54,6 +54,22 @@ static int input_side(const void* x, int N, int H, int W, int C, int k, int stri
   return 4;
 }
 
+// Filter-row halo form of a 3 x 3 / stride-1 tap table (see conv_tc.cu): one entry per filter COLUMN s, covering the
+// three taps of that column; entry.dh is the topmost input row offset (-1), k0(s) the K-column of the tap that reads
+// it and kstep the K-distance to the tap reading the next row down.
+static bool halo_ok(int nout, int64_t pixels) { return conv_halo_enabled() && nout % 256 != 0 && pixels > 128; }
+static void halo_taps_3x3(TapTable* taps, bool dgrad, int kc) {
+  memset(taps, 0, sizeof(*taps));
+  for (int s = 0; s < 3; ++s) {
+    taps->view[s] = 0;
+    taps->dh[s] = -1;
+    // fprop: tap (r, s) reads input (h + r - 1, w + s - 1), weights at (r * 3 + s) * Cin
+    // dgrad: tap (r, s) reads dy (h + 1 - r, w + 1 - s), weights at (r * 3 + s) * Cout: row offset -1 is r = 2
+    taps->dw[s] = (int8_t)(dgrad ? 1 - s : s - 1);
+    taps->koff[s] = (dgrad ? 6 + s : s) * kc;
+  }
+}
+
 }  // namespace peclr
 
 using namespace peclr;
@@ -77,6 +93,11 @@ extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, 
   const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
   if (nv < 0) return nv;
   View4 d = nhwc_view(y, N, Ho, Wo, Cout);
+  if (k == 3 && stride == 1 && halo_ok(Cout, (int64_t)N * Ho * Wo)) {
+    halo_taps_3x3(&taps, false, Cin);
+    return conv_gemm_launch(views, 1, w, (int64_t)9 * Cin, Cout, d, taps, 3, Cin / 64, stat_sum, stat_sumsq, 0, 0, st,
+                            nullptr, 3, 3 * Cin);
+  }
   return conv_gemm_launch(views, nv, w, (int64_t)num_taps * Cin, Cout, d, taps, num_taps, Cin / 64, stat_sum,
                           stat_sumsq, 0, 0, st);
 }
@@ -123,6 +144,11 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
         taps.koff[t] = t * Cout;
       }
     View4 d = nhwc_view(dx, N, H, W, Cin);
+    if (halo_ok(Cin, (int64_t)N * H * W)) {
+      halo_taps_3x3(&taps, true, Cout);
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 3, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
+                              bnr_for(d, &br), 3, -3 * Cout);
+    }
     return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
                             bnr_for(d, &br));
   }
@@ -221,6 +247,11 @@ extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, in
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
+  if (halo_ok(64, (int64_t)N * (H / 2) * (W / 2))) {  // the four filter rows as one tap group
+    taps.dh[0] = 0, taps.dw[0] = 0, taps.view[0] = 0, taps.koff[0] = 0;
+    return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 1, 1, stat_sum, stat_sumsq, 0, 0,
+                            static_cast<cudaStream_t>(stream), nullptr, 4, 64);
+  }
   return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0, 0,
                           static_cast<cudaStream_t>(stream));
 }

@@ -58,21 +58,32 @@ struct GemmParams {
   CUtensorMap y_map;
   const float *bn_mean, *bn_invstd, *bn_gamma, *bn_beta;
   int bn_reduce;
+  // filter-row halo mode (HALO kernels): a tap table entry is a GROUP of halo_taps taps that differ only in dh
+  // (dh = taps.dh[g] + t).  One (Hb + halo_taps - 1) x Wb input box per group and channel chunk serves all of them:
+  // tap t reads the same shared-memory buffer from row t * Wb on (Wb is a multiple of 8, so that offset is a
+  // multiple of the 1024-byte swizzle atom).  Tap t's weights sit halo_kstep columns after tap t - 1's.
+  int halo_taps, halo_kstep;
+  int halo_a_bytes, halo_stage_a, halo_stages;
   int stat_copies;  // 512 / BN private copies of the per-CTA statistics (one owner thread per address), or 1 (atomics)
 };
 
 // CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
 // 128 pixel rows of A and half of the BN weight rows, so the L2 -> shared-memory traffic per FLOP drops by a
 // third; the leader CTA issues the MMAs, each CTA drains its own 128 TMEM lanes.
-template <int BN, int STAGES, int CTAS>
+template <int BN, int STAGES, int CTAS, bool HALO = false>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kStageB = (BN / CTAS) * 128;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  // pipeline geometry: fixed for the per-tap kernels; in halo mode the A stage holds the taller box, the B stage
+  // one weight tile per tap of the group, and the number of stages is whatever fits (<= STAGES barriers)
+  const int n_stages = HALO ? p.halo_stages : STAGES;
+  const uint32_t stage_a = HALO ? (uint32_t)p.halo_stage_a : (uint32_t)kStageA;
+  const uint32_t stage_b = HALO ? (uint32_t)(p.halo_taps * kStageB) : (uint32_t)kStageB;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + STAGES * kStageA;
-  uint8_t* sD = sB + STAGES * kStageB;
+  uint8_t* sB = sA + n_stages * stage_a;
+  uint8_t* sD = sB + n_stages * stage_b;
   uint8_t* sY = sD + (BN / 64) * kStageA;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
   uint64_t* full = reinterpret_cast<uint64_t*>(sY + (p.bn_reduce ? (BN / 64) * kStageA : 0));
   uint64_t* empty = full + STAGES;
@@ -144,7 +155,24 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           const int kbase = p.taps.koff[tap];
           for (int c = 0; c < p.c_chunks; ++c) {
             mbar_wait(&empty[stage], phase ^ 1);
-            if constexpr (CTAS == 2) {
+            if constexpr (HALO) {
+              // one tall box for the whole tap group + one weight tile per tap
+              const uint32_t bytes = (uint32_t)p.halo_a_bytes + (uint32_t)p.halo_taps * kStageB;
+              uint8_t* dstA = sA + stage * stage_a;
+              uint8_t* dstB = sB + stage * stage_b;
+              if constexpr (CTAS == 2) {
+                if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * bytes);
+                tma_load_4d_2sm(amap, &full[stage], dstA, c * 64, cw, ch, n0);
+                for (int ht = 0; ht < p.halo_taps; ++ht)
+                  tma_load_2d_2sm(&p.b_map, &full[stage], dstB + ht * kStageB, kbase + ht * p.halo_kstep + c * 64,
+                                  nt * BN + cta_rank * (BN / 2));
+              } else {
+                mbar_expect_tx(&full[stage], bytes);
+                tma_load_4d(amap, &full[stage], dstA, c * 64, cw, ch, n0);
+                for (int ht = 0; ht < p.halo_taps; ++ht)
+                  tma_load_2d(&p.b_map, &full[stage], dstB + ht * kStageB, kbase + ht * p.halo_kstep + c * 64, nt * BN);
+              }
+            } else if constexpr (CTAS == 2) {
               // both CTAs' bytes are counted on the leader's barrier
               if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * (kStageA + kStageB));
               tma_load_4d_2sm(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
@@ -155,7 +183,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               tma_load_4d(amap, &full[stage], sA + stage * kStageA, c * 64, cw, ch, n0);
               tma_load_2d(&p.b_map, &full[stage], sB + stage * kStageB, kbase + c * 64, nt * BN);
             }
-            if (++stage == STAGES) {
+            if (++stage == n_stages) {
               stage = 0;
               phase ^= 1;
             }
@@ -185,16 +213,32 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * kStageA), 0, 1024);
-          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * kStageB), 0, 1024);
+          if constexpr (HALO) {
+            const uint32_t a0 = smem_u32(sA + stage * stage_a), b0 = smem_u32(sB + stage * stage_b);
+            const uint32_t row_bytes = (uint32_t)p.Wb * 128u;  // one image row of the box (multiple of 1024 B)
+            for (int ht = 0; ht < p.halo_taps; ++ht) {
+              const uint64_t a_desc = make_smem_desc(a0 + ht * row_bytes, 0, 1024);
+              const uint64_t b_desc = make_smem_desc(b0 + ht * kStageB, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the swizzle atom
-            if constexpr (CTAS == 2) umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if constexpr (CTAS == 2)
+                  umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | ht | k) != 0);
+                else
+                  umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | ht | k) != 0);
+              }
+            }
+          } else {
+            const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * kStageA), 0, 1024);
+            const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * kStageB), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels; +32 B per step inside the swizzle atom
+              if constexpr (CTAS == 2) umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           if constexpr (CTAS == 2) umma_commit_2sm(&empty[stage]);
           else umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -561,6 +605,7 @@ static EncodeTiledFn get_encode() {
 
 // rank-4 bf16 view (C, W, H, N); strides in elements for W, H, N; box (64, bw, bh, bn); 128B swizzle.
 static int encode_view(CUtensorMap* m, const View4& v, int bw, int bh, int bn) {
+  if (bw > 256 || bh > 256 || bn > 256) return PECLR_ERR_ARG;
   EncodeTiledFn enc = get_encode();
   if (!enc) return PECLR_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
@@ -617,6 +662,22 @@ void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn) {
     }
 }
 
+// Halo mode: one image per tile (Nb = 1) and a box width that is a multiple of 8 pixels, so that a shift by whole
+// image rows inside the shared-memory box keeps the 1024-byte swizzle-atom alignment.  Fewest tiles first, then the
+// tallest box (smallest halo overhead (bh + taps - 1) / bh).
+static void choose_box_halo(int W, int H, int* bw, int* bh) {
+  long best = -1;
+  for (int w = 8; w <= 128; w *= 2) {
+    const int h = 128 / w;
+    const long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h);
+    if (best < 0 || tiles < best || (tiles == best && h > *bh)) {
+      best = tiles;
+      *bw = w;
+      *bh = h;
+    }
+  }
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -628,19 +689,31 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CTAS>
+template <int BN, int STAGES, int CTAS, bool HALO = false>
 static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
   constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
-  size_t smem = 1024 + (size_t)STAGES * (kStageA + (BN / CTAS) * 128) +
-                (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256;
+  // everything but the pipeline stages: alignment slack, output staging (+ y tile), barriers
+  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256;
   p.stat_copies = 0;
   if (stats) {
     p.stat_copies = 512 / BN;
-    if (smem + (size_t)p.stat_copies * 2 * p.cout * 4 > kMaxSmem) p.stat_copies = 1;
+    const size_t stages_min = HALO ? 2 * ((size_t)p.halo_stage_a + (size_t)p.halo_taps * (BN / CTAS) * 128)
+                                   : (size_t)STAGES * (kStageA + (BN / CTAS) * 128);
+    if (smem + stages_min + (size_t)p.stat_copies * 2 * p.cout * 4 > kMaxSmem) p.stat_copies = 1;
     smem += (size_t)p.stat_copies * 2 * p.cout * 4;
   }
+  if constexpr (HALO) {
+    const size_t per_stage = (size_t)p.halo_stage_a + (size_t)p.halo_taps * (BN / CTAS) * 128;
+    int stages = (int)((kMaxSmem - smem) / per_stage);
+    if (stages > STAGES) stages = STAGES;
+    if (stages < 2) return PECLR_ERR_ARG;
+    p.halo_stages = stages;
+    smem += (size_t)stages * per_stage;
+  } else {
+    smem += (size_t)STAGES * (kStageA + (BN / CTAS) * 128);
+  }
   if (smem > kMaxSmem) return PECLR_ERR_ARG;
-  auto kern = conv_gemm_kernel<BN, STAGES, CTAS>;
+  auto kern = conv_gemm_kernel<BN, STAGES, CTAS, HALO>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -673,19 +746,43 @@ static bool use_cta_pairs() {
   return v != 0;
 }
 
+// The 3x3 / stride-1 convolutions with 64 or 128 output channels and the stem use the filter-row halo kernels
+// (measured -0.12 ms per ResNet-50 step on the same box; PECLR_CONV_HALO=0 selects the per-tap kernels for A/B runs).
+bool conv_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_CONV_HALO");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
                      const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
-                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr) {
+                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr,
+                     int halo_taps, int halo_kstep) {
   if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
   if (nout % 64 != 0 || ktot % 64 != 0 || d_view.c != nout) return PECLR_ERR_ARG;
   if (stat_sum && nout > 2048) return PECLR_ERR_ARG;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int bw = 1, bh = 1, bn = 1;
-  choose_box((int)d_view.w, (int)d_view.h, (int)d_view.n, 128, &bw, &bh, &bn);
+  const bool halo = halo_taps > 1;
+  if (halo) {
+    // (callers only group taps for nout in {64, 128}, more than one m tile, single-view stride-1 geometry)
+    if (nout % 256 == 0 || d_view.w * d_view.h * d_view.n <= 128 || !use_cta_pairs()) return PECLR_ERR_ARG;
+    choose_box_halo((int)d_view.w, (int)d_view.h, &bw, &bh);
+    p.halo_taps = halo_taps;
+    p.halo_kstep = halo_kstep;
+    p.halo_a_bytes = (bh + halo_taps - 1) * bw * 128;
+    p.halo_stage_a = (p.halo_a_bytes + 1023) / 1024 * 1024;
+  } else {
+    choose_box((int)d_view.w, (int)d_view.h, (int)d_view.n, 128, &bw, &bh, &bn);
+  }
   int rc;
   for (int i = 0; i < kMaxViews; ++i)
-    if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
+    if ((rc = encode_view(&p.a_maps[i], a_views[i < num_views ? i : 0], bw, halo ? bh + halo_taps - 1 : bh, bn)))
+      return rc;
   int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
   static int bn_max = -1;  // tuning knob: PECLR_CONV_BN_MAX caps the tile width (64 / 128 / 256)
   if (bn_max < 0) {
@@ -723,6 +820,11 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.stat_f32 = bnr != nullptr;  // forward BatchNorm sums are fp64; the fused BN-backward reduction uses fp32 sets
   p.reduce_add = reduce_add;
   const bool stats = stat_sum != nullptr;
+  if (halo) {
+    if (BN == 128) return launch_gemm_t<128, 8, 2, true>(p, stats, stream);
+    if (BN == 64) return launch_gemm_t<64, 8, 2, true>(p, stats, stream);
+    return PECLR_ERR_ARG;
+  }
   if (pairs) {
     if (BN == 256) return launch_gemm_t<256, 4, 2>(p, stats, stream);
     if (BN == 128) return launch_gemm_t<128, 6, 2>(p, stats, stream);

@@ -49,7 +49,11 @@ struct BnReduce {
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
                      const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
-                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr);
+                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr,
+                     int halo_taps = 0, int halo_kstep = 0);
+// halo_taps > 1: every tap-table entry is a group of halo_taps taps with dh = entry.dh + t (t = 0 .. halo_taps - 1),
+// whose weights are halo_kstep K-columns apart; the kernel loads one tall input box per group (see conv_tc.cu).
+bool conv_halo_enabled();
 
 // dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin)
 int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
