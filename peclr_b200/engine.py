@@ -355,11 +355,7 @@ class StepEngine:
         side, keep = self._side, []
         overlap = self.overlap_wgrad
 
-        skip_wgrad = os.environ.get("PECLR_DEBUG_SKIP_WGRAD", "0") == "1"  # timing experiments only (wrong grads)
-
         def wgrad(fn, *alive):
-            if skip_wgrad:
-                return
             if not overlap:
                 return fn()
             keep.extend(alive)
