@@ -260,6 +260,10 @@ def run_ours(args):
                 "wgrad_kernel": {"achieved": round(ach_w, 1), "frac": round(ach_w / pk["tf_sustained"], 4),
                                  "kernel_ms_per_step": round(times["wgrad"], 3)},
                 "step_conv_flop_frac": round(value * f_train / world / (pk["tf_sustained"] * 1e12), 4) if f_train else None}
+        try:  # (explanatory extra: never let it take the bench line down)
+            roof["per_launch_roofline"] = launch_bound_fraction(prof, pk["tf_sustained"], pk["hbm"])
+        except Exception as exc:  # pragma: no cover
+            roof["per_launch_roofline"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args, budget_s=20.0)
     if world > 1:
@@ -288,6 +292,43 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_bytes(name, a):
+    """Algorithmic HBM bytes of one conv launch from its C-ABI arguments: every operand once (bf16 activations and
+    weights; a read-modify-write of dx when the dgrad accumulates; the BatchNorm input tile of the fused reduction)."""
+    if name.startswith("peclr_stem"):
+        n, h, w = a[3], a[4], a[5]
+        return 2.0 * (n * (h // 2 + 3) * (w // 2 + 4) * 16 + n * (h // 2) * (w // 2) * 64 + 64 * 4 * 64)
+    n, h, w, cin, cout, k, s = a[3:10]
+    big, small = n * h * w * cin, n * (h // s) * (w // s) * cout  # input-side / output-side activation elements
+    total = big + small + cout * k * k * cin
+    if name == "peclr_conv2d_dgrad" and a[10]:
+        total += big
+    if name == "peclr_conv2d_dgrad_bnreduce":
+        total += big
+    return 2.0 * total
+
+
+def launch_bound_fraction(prof, peak_tflops, peak_gbs):
+    """Sum over the fprop / dgrad launches of max(FLOPs / tensor peak, algorithmic bytes / HBM peak), divided by the
+    sum of their measured durations: how close the kernel runs to the roofline of each individual launch (many of
+    them are 1x1 convolutions with K <= 256, which no kernel can run at the tensor peak)."""
+    bound = meas = 0.0
+    n_hbm = n_all = 0
+    for name, a, ms_k in prof:
+        if "wgrad" in name:
+            continue
+        t_tensor = conv_flops(name, a) / (peak_tflops * 1e12) * 1e3
+        t_hbm = conv_bytes(name, a) / (peak_gbs * 1e9) * 1e3
+        bound += max(t_tensor, t_hbm)
+        meas += ms_k
+        n_all += 1
+        n_hbm += t_hbm > t_tensor
+    if meas <= 0:
+        return None
+    return {"bound_ms": round(bound, 3), "measured_ms": round(meas, 3), "frac": round(bound / meas, 4),
+            "launches": n_all, "hbm_bound_launches": n_hbm}
 
 
 def conv_flops(name, a):

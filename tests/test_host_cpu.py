@@ -190,3 +190,28 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1"})
     assert r1.returncode == 0 and r1.stdout.strip() == ""  # other ranks exit without work
+
+
+def test_bench_roofline_arithmetic():
+    """bench.py's per-launch FLOP / byte accounting: 2MNK of a conv launch, every operand once."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fprop = ("peclr_conv2d_fprop", (0, 0, 0, 256, 56, 56, 64, 256, 1, 1, 0, 0, 0))
+    assert bench.conv_flops(*fprop) == 2.0 * 256 * 56 * 56 * 256 * 64
+    assert bench.conv_bytes(*fprop) == 2.0 * (256 * 56 * 56 * (64 + 256) + 256 * 64)
+    acc = ("peclr_conv2d_dgrad", (0, 0, 0, 256, 56, 56, 256, 64, 1, 1, 1, 0))
+    plain = ("peclr_conv2d_dgrad", (0, 0, 0, 256, 56, 56, 256, 64, 1, 1, 0, 0))
+    assert bench.conv_bytes(*acc) - bench.conv_bytes(*plain) == 2.0 * 256 * 56 * 56 * 256  # read-modify-write of dx
+    stem = ("peclr_stem_fprop", (0, 0, 0, 256, 224, 224, 0, 0, 0))
+    assert bench.conv_flops(*stem) == 2.0 * 256 * 112 * 112 * 64 * 147
+    # the whole ResNet-50 @ 224 figure of SURVEY 8(d) is 24.287 GFLOP per image: one 3x3 256->256 @14x14 is 0.2312 of it
+    c3 = ("peclr_conv2d_fprop", (0, 0, 0, 1, 14, 14, 256, 256, 3, 1, 0, 0, 0))
+    assert abs(bench.conv_flops(*c3) / 1e6 - 2 * 115.6) < 0.1  # table A2: 115.6 MMAC per image
+    rec = [fprop + (0.10,), acc + (0.16,), ("peclr_conv2d_wgrad", (0,) * 11, 0.5)]
+    out = bench.launch_bound_fraction(rec, 1362.3, 6540.8)
+    assert out["launches"] == 2 and out["hbm_bound_launches"] == 2 and 0 < out["frac"] < 1
+    assert bench.F_TRAIN[("50", 224)] == 24.287e9 and bench.F_TRAIN[("152", 224)] == 68.834e9
