@@ -76,6 +76,7 @@ class ModelCheckpoint(Callback):
         self.best: List[tuple] = []  # (value, path)
 
     def _save_model(self, filepath: str, trainer, pl_module):
+        print(f"Saving checkpoint at {filepath}")  # (UpdatedModelCheckpoint, callbacks/model_checkpoint.py:5-10)
         os.makedirs(os.path.dirname(filepath), exist_ok=True)
         ckpt = {
             "epoch": trainer.current_epoch,
@@ -135,7 +136,8 @@ class JsonlLogger:
 class Trainer:
     def __init__(self, accumulate_grad_batches=1, gpus=None, logger=None, max_epochs=1, precision=16,
                  amp_backend="native", callbacks=None, checkpoint_callback=None, default_root_dir=None,
-                 limit_train_batches=None, limit_val_batches=None, log_every_n_steps=50, use_cuda_graph=True):
+                 limit_train_batches=None, limit_val_batches=None, log_every_n_steps=50, use_cuda_graph=True,
+                 resume_from_checkpoint=None):
         self.accumulate_grad_batches = accumulate_grad_batches
         self.max_epochs = max_epochs
         self.logger = logger
@@ -147,6 +149,7 @@ class Trainer:
         self.limit_train_batches, self.limit_val_batches = limit_train_batches, limit_val_batches
         self.log_every_n_steps = log_every_n_steps
         self.use_cuda_graph = use_cuda_graph
+        self.resume_from_checkpoint = resume_from_checkpoint  # path of an ``epoch=N.ckpt`` written by ModelCheckpoint
         # precision: the trunk computes in bf16 on the tensor cores with fp32 accumulation / master weights; the
         # reference's fp16 AMP + GradScaler (precision=16) has no counterpart to configure here.
         self.precision = precision
@@ -162,6 +165,19 @@ class Trainer:
     def _to_device(self, batch, device):
         return {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
 
+    def restore(self, path: str, model: LightningModule) -> int:
+        """Loads a checkpoint written by ModelCheckpoint (Lightning's layout: state_dict, optimizer_states,
+        lr_schedulers, epoch, global_step) into the model and this trainer's optimiser / scheduler.  Returns the epoch
+        to continue with.  A checkpoint without optimiser state (e.g. written by the reference) restores weights only."""
+        ckpt = torch.load(path, map_location="cpu")
+        model.load_state_dict(ckpt["state_dict"])
+        for opt, sd in zip(self.optimizers, ckpt.get("optimizer_states", [])):
+            opt.load_state_dict(sd)
+        for sch, sd in zip(self.lr_schedulers, ckpt.get("lr_schedulers", [])):
+            sch["scheduler"].load_state_dict(sd)
+        self.global_step = int(ckpt.get("global_step", 0))
+        return int(ckpt.get("epoch", -1)) + 1
+
     def fit(self, model: LightningModule, train_dataloader, val_dataloader=None):
         device = torch.device("cuda", torch.cuda.current_device())
         model.trainer = self
@@ -174,8 +190,9 @@ class Trainer:
         opt, sched = opts[0], scheds[0]["scheduler"]
         acc = self.accumulate_grad_batches
         graphed = None
+        first_epoch = self.restore(self.resume_from_checkpoint, model) if self.resume_from_checkpoint else 0
         opt.zero_grad()
-        for epoch in range(self.max_epochs):
+        for epoch in range(first_epoch, self.max_epochs):
             self.current_epoch = epoch
             model.train()
             outputs = []

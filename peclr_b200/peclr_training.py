@@ -75,9 +75,20 @@ def main(argv=None):
     logger = JsonlLogger(save_dir, experiment_name) if rank == 0 else None
     if args.meta_file is not None and rank == 0:
         save_experiment_key(experiment_name, logger.get_key(), args.meta_file)
+    # checkpoints: $SAVED_MODELS_BASE_PATH/<experiment key>/checkpoints/epoch=N.ckpt when that variable is set (the
+    # layout get_latest_checkpoint / restore_model read, src/models/utils.py:189-206), else <root dir>/checkpoints;
+    # -experiment_key [-checkpoint epoch=N.ckpt] resumes from such a directory (weights, optimiser, schedule, epoch)
+    models_base = os.environ.get("SAVED_MODELS_BASE_PATH")
+    if models_base and logger is not None:
+        callbacks["checkpoint_callback"].dirpath = os.path.join(models_base, logger.get_key(), "checkpoints")
+    resume = None
+    if args.experiment_key:
+        from .model_utils import get_latest_checkpoint
+
+        resume = get_latest_checkpoint(args.experiment_key, args.checkpoint)
     trainer = Trainer(accumulate_grad_batches=train_param.accumulate_grad_batches, gpus="0", logger=logger,
                       max_epochs=train_param.epochs, precision=train_param.precision, amp_backend="native",
-                      limit_train_batches=args.limit_train_batches, **callbacks)
+                      limit_train_batches=args.limit_train_batches, resume_from_checkpoint=resume, **callbacks)
     trainer.fit(model, train_loader, val_loader if len(val_loader) > 0 else None)
     if rank == 0:
         loss = float(model.train_metrics_epoch.get("loss", float("nan")))

@@ -215,3 +215,43 @@ def test_bench_roofline_arithmetic():
     out = bench.launch_bound_fraction(rec, 1362.3, 6540.8)
     assert out["launches"] == 2 and out["hbm_bound_launches"] == 2 and 0 < out["frac"] < 1
     assert bench.F_TRAIN[("50", 224)] == 24.287e9 and bench.F_TRAIN[("152", 224)] == 68.834e9
+
+
+def test_checkpoint_save_and_trainer_restore(model, tmp_path):
+    """ModelCheckpoint's file (Lightning layout) -> Trainer.restore: weights, Adam moments / step count, scheduler
+    position and the epoch to continue with (reference: UpdatedModelCheckpoint + PL resume)."""
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.hybrid2_model import Hybrid2Model
+    from peclr_b200.lightning import ModelCheckpoint, Trainer
+
+    def prepared(m):
+        tr = Trainer(max_epochs=100, default_root_dir=str(tmp_path))
+        m.trainer = tr
+        m.setup("fit")
+        tr.optimizers, tr.lr_schedulers = m.configure_optimizers()
+        return tr
+
+    tr = prepared(model)
+    opt, sch = tr.optimizers[0], tr.lr_schedulers[0]["scheduler"]
+    eng = model.engine
+    eng.exp_avg, eng.exp_avg_sq = torch.full_like(eng.flat, 0.125), torch.full_like(eng.flat, 0.5)
+    opt.step_count = 7
+    for _ in range(5):
+        sch.step()
+    tr.current_epoch, tr.global_step = 3, 7
+    path = str(tmp_path / "checkpoints" / "epoch=3.ckpt")
+    ModelCheckpoint()._save_model(path, tr, model)
+    ckpt = torch.load(path, map_location="cpu")
+    assert set(ckpt) >= {"epoch", "global_step", "state_dict", "optimizer_states", "lr_schedulers"}
+    assert list(ckpt["state_dict"].keys()) == list(model.state_dict().keys())
+
+    torch.manual_seed(1)
+    other = Hybrid2Model(EasyDict(dict(po.default_config(resnet_size="50", batch_size=8, num_samples=8 * 64))))
+    tr2 = prepared(other)
+    assert tr2.restore(path, other) == 4 and tr2.global_step == 7
+    for (k, a), b in zip(model.state_dict().items(), other.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert tr2.optimizers[0].step_count == 7
+    assert float(other.engine.exp_avg[0]) == 0.125 and float(other.engine.exp_avg_sq[-1]) == 0.5
+    assert tr2.lr_schedulers[0]["scheduler"].last_epoch == sch.last_epoch == 5
+    assert tr2.optimizers[0].param_groups[0]["lr"] == pytest.approx(opt.param_groups[0]["lr"])
