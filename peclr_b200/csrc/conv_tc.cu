@@ -752,7 +752,7 @@ bool conv_halo_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PECLR_CONV_HALO");
-    v = e ? atoi(e) : 1;
+    v = (e ? atoi(e) : 1) != 0 && use_cta_pairs();  // the halo kernels exist as CTA-pair kernels only
   }
   return v != 0;
 }
