@@ -163,6 +163,16 @@ def load_reference():
         simclr = importlib.import_module("src.models.unsupervised.simclr_model")
         hybrid2 = importlib.import_module("src.models.unsupervised.hybrid2_model")
         port = importlib.import_module("src.models.port_model")
+        # flag surface / config merging / experiment naming (src/experiments/utils.py); its import chain reaches the
+        # data loaders, which still use the torch 1.7 module path ``torch.tensor``
+        if "torch.tensor" not in sys.modules:
+            import torch
+
+            sys.modules["torch.tensor"] = _module("torch.tensor", Tensor=torch.Tensor)
+        try:
+            exp_utils = importlib.import_module("src.experiments.utils")
+        except Exception:  # pragma: no cover  (optional: only the CLI pinning test needs it)
+            exp_utils = None
         # base_model.py:23 hard-codes pretrained=True (needs network) -> force False.
         orig = mutils.get_wrapper_model
         base.get_wrapper_model = lambda config, pretrained, wrapper=False: orig(config, False, wrapper)
@@ -172,6 +182,7 @@ def load_reference():
             simclr_model=simclr,
             hybrid2_model=hybrid2,
             port_model=port,
+            experiments_utils=exp_utils,
             Hybrid2Model=hybrid2.Hybrid2Model,
             SimCLR=simclr.SimCLR,
             vanila_contrastive_loss=mutils.vanila_contrastive_loss,

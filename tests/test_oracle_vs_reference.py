@@ -57,3 +57,65 @@ def test_ops_identical(ref):
     assert torch.equal(ref.translate_encodings(enc.clone(), tx, ty), po.translate_encodings(enc.clone(), tx, ty))
     z = torch.nn.functional.normalize(torch.randn(16, 128, generator=g))
     assert torch.equal(ref.vanila_contrastive_loss(z[:8], z[8:]), po.vanila_contrastive_loss(z[:8], z[8:]))
+
+
+def test_cli_config_and_naming_identical_to_reference(ref, monkeypatch):
+    """The reference's own get_general_args / update_train_params / update_model_params / prepare_name
+    (src/experiments/utils.py:29-163,276-393,608-615), executed, against this build's mirror of them."""
+    import json
+    import os
+    import sys
+
+    from peclr_b200 import experiments_utils as ours
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.peclr_training import HYBRID2_CONFIG, TRAINING_CONFIG_PATH
+
+    theirs = ref.experiments_utils
+    assert theirs is not None, "src.experiments.utils of the reference did not import"
+    ref_cfg = "/root/reference/src/experiments/config"
+    def no_aug(d):  # (this build ships only the augmentation_params the synthetic generator uses: a subset)
+        return {k: v for k, v in json.loads(json.dumps(d)).items() if k != "augmentation_params"}
+
+    for mine, name in ((TRAINING_CONFIG_PATH, "training_config.json"), (HYBRID2_CONFIG, "hybrid2_config.json")):
+        a, b = json.load(open(mine)), json.load(open(os.path.join(ref_cfg, name)))
+        assert no_aug(a) == no_aug(b), name  # same shipped defaults
+        for k, v in a.get("augmentation_params", {}).items():
+            assert b["augmentation_params"][k] == v, k
+    argvs = [
+        [],
+        ["--rotate", "--crop", "-resnet_size", "50", "-epochs", "100", "-batch_size", "128", "-accumulate_grad_batches",
+         "16", "-save_top_k", "1", "-save_period", "1", "-num_workers", "8"],  # README.md:51 of the reference
+        ["--color_jitter", "--random_crop", "--rotate", "--crop", "--resize", "-resnet_size", "152", "-sources",
+         "freihand", "-sources", "youtube", "-lr", "0.001", "-optimizer", "adam", "-seed", "7", "-lr_max_epochs", "50",
+         "-tag", "a", "-tag", "b", "-train_ratio", "0.9", "-log_interval", "step", "-meta_file", "m.csv"],
+    ]
+    for argv in argvs:
+        monkeypatch.setattr(sys, "argv", ["peclr_training.py"] + argv)
+        a_ref = vars(theirs.get_general_args("Hybrid model 2 training script."))
+        a_our = vars(ours.get_general_args("Hybrid model 2 training script.", argv))
+        for k, v in a_ref.items():  # every reference flag exists here with the same parsed value / default
+            assert k in a_our and a_our[k] == v, (argv, k, v, a_our.get(k))
+        t_ref = theirs.update_train_params(theirs.get_general_args("x"),
+                                           ref.EasyDict(json.load(open(os.path.join(ref_cfg, "training_config.json")))))
+        t_our = ours.update_train_params(ours.get_general_args("x", argv), EasyDict(json.load(open(TRAINING_CONFIG_PATH))))
+        assert no_aug(t_ref) == no_aug(t_our), argv
+        m_ref = theirs.update_model_params(ref.EasyDict(json.load(open(HYBRID2_CONFIG))), theirs.get_general_args("x"),
+                                           4321, t_ref)
+        m_our = ours.update_model_params(EasyDict(json.load(open(HYBRID2_CONFIG))), ours.get_general_args("x", argv),
+                                         4321, t_our)
+        assert json.loads(json.dumps(m_ref)) == json.loads(json.dumps(m_our)), argv
+        assert theirs.prepare_name("hybrid2_", t_ref) == ours.prepare_name("hybrid2_", t_our)
+    both = dict(batch_size=64, pairwise={"augmentation_flags": {"crop": True, "rotate": True, "flip": False}},
+                contrastive={"augmentation_flags": {"color_jitter": True, "gaussian_blur": True}})
+    assert theirs.prepare_name("hybrid1_", ref.EasyDict(both), True) == ours.prepare_name("hybrid1_", EasyDict(both), True)
+
+
+def test_translate2_and_rotation_matrix_identical(ref):
+    g = torch.Generator().manual_seed(12)
+    enc = torch.randn(5, 64, 2, generator=g)
+    tx, ty = torch.rand(5, generator=g), torch.rand(5, generator=g)
+    want = ref.utils.translate_encodings2(enc.clone(), tx, ty)
+    assert torch.equal(want, enc + torch.stack([tx, ty], dim=1)[:, None, :])  # what the CUDA op is tested against
+    ang = torch.floor(torch.rand(5, generator=g, dtype=torch.float64) * 90 - 45)
+    cx, cy = torch.randn(5, generator=g), torch.randn(5, generator=g)
+    assert torch.equal(ref.get_rotation_2D_matrix(ang, cx, cy, 1.0), po.get_rotation_2D_matrix(ang, cx, cy, 1.0))
