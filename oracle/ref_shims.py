@@ -171,8 +171,9 @@ def load_reference():
             sys.modules["torch.tensor"] = _module("torch.tensor", Tensor=torch.Tensor)
         try:
             exp_utils = importlib.import_module("src.experiments.utils")
-        except Exception:  # pragma: no cover  (optional: only the CLI pinning test needs it)
-            exp_utils = None
+            augmenter = importlib.import_module("src.data_loader.sample_augmenter")
+        except Exception:  # pragma: no cover  (optional: only the CLI / batch-contract pinning tests need them)
+            exp_utils = augmenter = None
         # base_model.py:23 hard-codes pretrained=True (needs network) -> force False.
         orig = mutils.get_wrapper_model
         base.get_wrapper_model = lambda config, pretrained, wrapper=False: orig(config, False, wrapper)
@@ -183,6 +184,7 @@ def load_reference():
             hybrid2_model=hybrid2,
             port_model=port,
             experiments_utils=exp_utils,
+            sample_augmenter=augmenter,
             Hybrid2Model=hybrid2.Hybrid2Model,
             SimCLR=simclr.SimCLR,
             vanila_contrastive_loss=mutils.vanila_contrastive_loss,

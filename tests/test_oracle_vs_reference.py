@@ -119,3 +119,47 @@ def test_translate2_and_rotation_matrix_identical(ref):
     ang = torch.floor(torch.rand(5, generator=g, dtype=torch.float64) * 90 - 45)
     cx, cy = torch.randn(5, generator=g), torch.randn(5, generator=g)
     assert torch.equal(ref.get_rotation_2D_matrix(ang, cx, cy, 1.0), po.get_rotation_2D_matrix(ang, cx, cy, 1.0))
+
+
+def test_batch_contract_matches_executed_augmenter(ref):
+    """what the reference's SampleAugmenter really emits for the per-sample correction parameters
+    (executed here on a synthetic image + joints with the reference's own training_config.json), against the
+    synthetic two-view generator that replaces src/data_loader: angle = integer-valued python float in [-45, 45)
+    -> float64 after collation, jitter_x / jitter_y = python int in {-14..0} -> int64."""
+    import json
+    import random
+
+    from peclr_b200.synthetic import SyntheticTwoViewDataset, synthetic_batch
+
+    assert ref.sample_augmenter is not None
+    cfg = json.load(open("/root/reference/src/experiments/config/training_config.json"))
+    flags = ref.EasyDict(cfg["augmentation_flags"])
+    flags.crop = flags.rotate = flags.resize = True
+    aug = ref.sample_augmenter.SampleAugmenter(flags, ref.EasyDict(cfg["augmentation_params"]))
+    random.seed(0)
+    g = torch.Generator().manual_seed(0)
+    img = (np.random.RandomState(0).rand(224, 224, 3) * 255).astype(np.uint8)
+    angles, jit = [], []
+    for _ in range(300):
+        joints = torch.rand(21, 3, generator=g) * 60 + 80  # a hand well inside the image: no clipping at the edge
+        out_img, _, _ = aug.transform_sample(img, joints)
+        assert out_img.shape == (128, 128, 3)  # resize_shape of the reference config
+        angles.append(aug.angle)
+        jit += [aug.jitter_x, aug.jitter_y]
+    assert all(isinstance(a, float) and float(a).is_integer() for a in angles) and all(isinstance(j, int) for j in jit)
+    assert -45 <= min(angles) and max(angles) <= 44 and min(jit) >= -14 and max(jit) <= 0
+    collated = torch.utils.data.default_collate([{"angle_1": angles[0], "jitter_x_1": jit[0]},
+                                                 {"angle_1": angles[1], "jitter_x_1": jit[2]}])
+    assert collated["angle_1"].dtype == torch.float64 and collated["jitter_x_1"].dtype == torch.int64
+    # the synthetic generator covers the same value sets with the same dtypes, batched and per sample
+    b = synthetic_batch(512, 8, seed=1)
+    for k in (1, 2):
+        a = b[f"angle_{k}"]
+        assert a.dtype == torch.float64 and torch.equal(a, a.floor()) and -45 <= a.min() and a.max() <= 44
+        for ax in "xy":
+            j = b[f"jitter_{ax}_{k}"]
+            assert j.dtype == torch.int64 and -14 <= j.min() and j.max() <= 0
+    assert set(angles) <= set(b["angle_1"].tolist()) | set(b["angle_2"].tolist()) | set(float(v) for v in range(-45, 45))
+    item = torch.utils.data.default_collate([SyntheticTwoViewDataset(4, 8)[i] for i in range(2)])
+    assert item["angle_1"].dtype == torch.float64 and item["jitter_y_2"].dtype == torch.int64
+    assert item["transformed_image1"].shape == (2, 3, 8, 8) and item["transformed_image1"].dtype == torch.float32
