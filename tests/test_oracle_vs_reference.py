@@ -163,3 +163,41 @@ def test_batch_contract_matches_executed_augmenter(ref):
     item = torch.utils.data.default_collate([SyntheticTwoViewDataset(4, 8)[i] for i in range(2)])
     assert item["angle_1"].dtype == torch.float64 and item["jitter_y_2"].dtype == torch.int64
     assert item["transformed_image1"].shape == (2, 3, 8, 8) and item["transformed_image1"].dtype == torch.float32
+
+
+def test_epoch_hooks_and_schedule_setup_identical(ref):
+    """BaseModel.setup / training_epoch_end / validation_epoch_end / exclude_from_wt_decay (base_model.py:30-55,106-127)
+    executed on the reference class against this build's BaseModel (host logic, CPU)."""
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.hybrid2_model import Hybrid2Model
+
+    cfg = po.default_config(resnet_size="18", batch_size=16, num_samples=16 * 37 + 5, projection_head_input_dim=512)
+    torch.manual_seed(0)
+    theirs = ref.Hybrid2Model(ref.EasyDict(dict(cfg)))
+    torch.manual_seed(0)
+    ours = Hybrid2Model(EasyDict(dict(cfg)))
+    logged = {}
+    theirs.log = lambda name, value, **kw: logged.__setitem__(name, value)
+    for world in (1, 2, 8):
+        theirs.trainer = po._TrainerStub(world_size=world, max_epochs=50)
+        ours.trainer = po._TrainerStub(world_size=world, max_epochs=50)
+        theirs.setup("fit"), ours.setup("fit")
+        assert theirs.train_iters_per_epoch == ours.train_iters_per_epoch == (16 * 37 + 5) // (16 * world)
+    g = torch.Generator().manual_seed(3)
+    outputs = [{"loss": torch.rand((), generator=g), "proj1x_mean": torch.randn((), generator=g)} for _ in range(7)]
+    theirs.training_epoch_end(outputs), ours.training_epoch_end(outputs)
+    assert set(theirs.train_metrics_epoch) == set(ours.train_metrics_epoch)
+    for k in theirs.train_metrics_epoch:
+        assert torch.equal(theirs.train_metrics_epoch[k], ours.train_metrics_epoch[k]), k
+    assert torch.equal(logged["checkpoint_saving_loss"], ours._logged["checkpoint_saving_loss"])
+    theirs.validation_epoch_end(outputs), ours.validation_epoch_end(outputs)
+    assert torch.equal(theirs.validation_metrics_epoch["loss"], ours.validation_metrics_epoch["loss"])
+    # weight-decay groups: same parameter NAMES in the decayed / excluded groups
+    def names(model, groups):
+        by_id = {id(p): n for n, p in model.named_parameters()}
+        return [[by_id[id(p)] for p in grp["params"]] for grp in groups]
+
+    g1 = theirs.exclude_from_wt_decay(theirs.named_parameters(), weight_decay=1e-6)
+    g2 = ours.exclude_from_wt_decay(ours.named_parameters(), weight_decay=1e-6)
+    assert names(theirs, g1) == names(ours, g2)
+    assert [grp["weight_decay"] for grp in g1] == [grp["weight_decay"] for grp in g2] == [1e-6, 0.0]
