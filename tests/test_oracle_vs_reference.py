@@ -201,3 +201,40 @@ def test_epoch_hooks_and_schedule_setup_identical(ref):
     g2 = ours.exclude_from_wt_decay(ours.named_parameters(), weight_decay=1e-6)
     assert names(theirs, g1) == names(ours, g2)
     assert [grp["weight_decay"] for grp in g1] == [grp["weight_decay"] for grp in g2] == [1e-6, 0.0]
+
+
+def test_checkpoint_helpers_identical(ref, monkeypatch, tmp_path):
+    """get_latest_checkpoint / get_encoder_state_dict (src/models/utils.py:189-225), get_checkpoints / restore_model
+    (src/experiments/utils.py:535-561) executed on the same checkpoint directory as this build's versions."""
+    import os
+
+    from peclr_b200 import experiments_utils as eu
+    from peclr_b200 import model_utils as mu
+
+    base = ref.utils.SAVED_MODELS_BASE_PATH  # captured by the reference at import time
+    monkeypatch.setenv("SAVED_MODELS_BASE_PATH", base)
+    key = "pin_%d" % os.getpid()
+    ckpt_dir = os.path.join(base, key, "checkpoints")
+    os.makedirs(ckpt_dir, exist_ok=True)
+    sd = {"encoder.features.0.weight": torch.randn(2, 3), "projection_head.0.bias": torch.randn(4),
+          "encoder.final_layer.0.bias": torch.randn(3)}
+    try:
+        for epoch in (2, 10, 9):
+            torch.save({"state_dict": {k: v + epoch for k, v in sd.items()}, "epoch": epoch},
+                       os.path.join(ckpt_dir, f"epoch={epoch}.ckpt"))
+        assert ref.utils.get_latest_checkpoint(key) == mu.get_latest_checkpoint(key)
+        assert mu.get_latest_checkpoint(key).endswith("epoch=10.ckpt")  # by the integer, not lexicographically
+        assert ref.utils.get_latest_checkpoint(key, "epoch=2.ckpt") == mu.get_latest_checkpoint(key, "epoch=2.ckpt")
+        e1, e2 = ref.utils.get_encoder_state_dict(key, ""), mu.get_encoder_state_dict(key, "")
+        assert list(e1) == list(e2) == ["features.0.weight", "final_layer.0.bias"]
+        assert all(torch.equal(e1[k], e2[k]) for k in e1)
+        assert ref.experiments_utils.get_checkpoints(key, 2) == eu.get_checkpoints(key, 2)
+        m1, m2 = torch.nn.Linear(3, 2, bias=False), torch.nn.Linear(3, 2, bias=False)
+        full = {"weight": torch.randn(2, 3)}
+        torch.save({"state_dict": full}, os.path.join(ckpt_dir, "epoch=11.ckpt"))
+        ref.experiments_utils.restore_model(m1, key), eu.restore_model(m2, key)
+        assert torch.equal(m1.weight, m2.weight) and torch.equal(m2.weight.detach(), full["weight"])
+    finally:
+        for f in os.listdir(ckpt_dir):
+            os.remove(os.path.join(ckpt_dir, f))
+        os.removedirs(ckpt_dir)
