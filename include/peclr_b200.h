@@ -20,6 +20,7 @@
 extern "C" {
 #endif
 
+/* 2 = this header (1: fp32 statistic sums, NHWC4 stem input) */
 int peclr_abi_version(void);
 /* R = number of accumulator sets in a BN-backward "scratch" buffer: where a scratch is documented as [2C] it is
  * float[R][2C]; block b adds into set b % R and the consumer adds the sets in order (fewer atomics serialised on

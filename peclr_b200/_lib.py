@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PECLR_B200_LIB: load another build of the same ABI (A/B timing of kernel changes); never a fallback
 LIB_PATH = os.environ.get("PECLR_B200_LIB") or os.path.join(_HERE, "libpeclr_b200.so")
 
+ABI_VERSION = 2  # include/peclr_b200.h
+
 P = c_void_p
 I = c_int
 L = c_longlong
@@ -79,6 +81,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, c_int)
+    if lib.peclr_abi_version() != ABI_VERSION:
+        raise PeclrKernelError(f"{LIB_PATH} implements ABI version {lib.peclr_abi_version()}, this binding needs "
+                               f"{ABI_VERSION}: rebuild it (python -m peclr_b200.build --force)")
     _lib = lib
     return lib
 

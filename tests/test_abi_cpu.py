@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     lib = ctypes.CDLL(lib_path)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.peclr_abi_version() == 1
+    assert lib.peclr_abi_version() == 2
 
 
 def test_python_binding_matches_header(lib_path):
