@@ -1,6 +1,9 @@
 #!/bin/bash
 # usage: scripts/build_rev_lib.sh <git-rev>   -> peclr_b200/libpeclr_b200_old.so built from that revision's csrc/
 # (A/B timing on one GPU box: PECLR_B200_LIB=$PWD/peclr_b200/libpeclr_b200_old.so python bench.py ...)
+# Works between revisions of the SAME ABI version (the binding refuses another one); across an ABI change, export the
+# whole old tree instead: mkdir ab_old && git archive <rev> | tar -x -C ab_old && (cd ab_old && python -m peclr_b200.build)
+# and run bench.py in both directories (ab_old/ is git-ignored and travels with gpurun).
 set -e
 rev=${1:-HEAD}
 root=$(cd "$(dirname "$0")/.." && pwd)
