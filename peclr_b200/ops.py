@@ -312,8 +312,8 @@ def ntxent_plain(z, temperature=0.5, want_grad=True, workspace=None):
     return loss, None, g
 
 
-# ------------------------------------------------------------------ optimiser plumbing
-# ---- stand-alone equivariance operators (csrc/equiv_ops.cu); reference src/models/utils.py:271-364 -------------
+# ------------------------------------------------------------------ stand-alone equivariance operators
+# (csrc/equiv_ops.cu; reference src/models/utils.py:271-364, hybrid2_model.py:92-106)
 def _per_sample(v, n, dtype, device, name):
     v = torch.as_tensor(v, device=device).reshape(-1).to(dtype).contiguous()
     if v.numel() != n:
@@ -372,6 +372,7 @@ def projection_stats(proj):
     return out
 
 
+# ------------------------------------------------------------------ optimiser plumbing
 def build_opt_tables(seg_sizes, seg_wd, device):
     """Flat-buffer segment / chunk tables for peclr_lars_adam_step."""
     chunk = _lib.call("peclr_opt_chunk_elems")
