@@ -141,24 +141,24 @@ static int check_launch() {
 
 extern "C" int peclr_translate_encodings(float* enc, const float* tx, const float* ty, int n, int m, int d, int exact,
                                          void* stream) {
+  if (n == 0) return 0;  // empty batch: nothing to do (null pointers are fine then)
   if (!enc || !tx || !ty || n < 0 || m < 1 || d < 2) return -1001;
-  if (n == 0) return 0;
   translate_encodings_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0,
                                static_cast<cudaStream_t>(stream)>>>(enc, tx, ty, n, m, d, exact ? 1 : 0);
   return check_launch();
 }
 
 extern "C" int peclr_rotate_encoding(float* enc, const double* angle, float* rot, int n, int m, int d, void* stream) {
-  if (!enc || !angle || n < 0 || m < 1 || d < 2) return -1001;
   if (n == 0) return 0;
+  if (!enc || !angle || n < 0 || m < 1 || d < 2) return -1001;
   rotate_encoding_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0,
                            static_cast<cudaStream_t>(stream)>>>(enc, angle, rot, n, m, d);
   return check_launch();
 }
 
 extern "C" int peclr_rotate_encoding_bwd(float* g, const float* rot, int n, int m, int d, void* stream) {
-  if (!g || !rot || n < 0 || m < 1 || d < 2) return -1001;
   if (n == 0) return 0;
+  if (!g || !rot || n < 0 || m < 1 || d < 2) return -1001;
   rotate_encoding_bwd_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0,
                                static_cast<cudaStream_t>(stream)>>>(g, rot, n, m, d);
   return check_launch();
@@ -166,8 +166,8 @@ extern "C" int peclr_rotate_encoding_bwd(float* g, const float* rot, int n, int 
 
 extern "C" int peclr_rotation_2d_matrix(const double* angle, const float* center_x, const float* center_y,
                                         double scale, float* out, int n, void* stream) {
-  if (!angle || !center_x || !center_y || !out || n < 0) return -1001;
   if (n == 0) return 0;
+  if (!angle || !center_x || !center_y || !out || n < 0) return -1001;
   rotation_matrix_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(angle, center_x, center_y,
                                                                                         scale, out, n);
   return check_launch();
