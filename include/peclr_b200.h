@@ -20,12 +20,15 @@
 extern "C" {
 #endif
 
-/* 2 = this header (1: fp32 statistic sums, NHWC4 stem input) */
+/* 3 = this header (1: fp32 statistic sums, NHWC4 stem input; 2: fp64 forward sums, fp32 accumulator-set scratch,
+ * atomically reduced weight-gradient splits).
+ *
+ * Reproducibility contract of version 3: no result depends on the order in which thread blocks run.  Per-channel
+ * sums (forward BatchNorm statistics, BN-backward sums, optimiser norms, loss-chain row sums) are fp64 accumulators
+ * receiving one partial per block, each partial computed in a fixed order; split-K partial products (weight
+ * gradients, head GEMMs, the loss chain's gradient) go through workspace slabs that are added in slab order.  Two
+ * runs on the same inputs give bit-identical loss, gradients and updated weights. */
 int peclr_abi_version(void);
-/* R = number of accumulator sets in a BN-backward "scratch" buffer: where a scratch is documented as [2C] it is
- * float[R][2C]; block b adds into set b % R and the consumer adds the sets in order (fewer atomics serialised on
- * one address). */
-int peclr_stat_replicas(void);
 
 /* ---- ResNet trunk convolutions: tcgen05/TMEM implicit GEMM fed by TMA (csrc/conv_tc.cu) ------------
  * Replace nn.Conv2d forward/backward inside ResNetModel.features
@@ -46,21 +49,27 @@ int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, i
                        int stride, int accumulate, void* stream);
 /* The same dgrad with the BatchNorm-backward reduction of the BN + ReLU sitting in front of this convolution fused
  * into the epilogue: bn_y = that BatchNorm's input (shape of dx), bn_* its saved mean / invstd and affine
- * parameters; scratch[0:Cin] = sum g, scratch[Cin:2Cin] = sum g*y with g = dx * relu'  (what peclr_bn_bwd_reduce
- * with mask_mode 2 computes in a separate pass).  Follow with peclr_bn_bwd_apply(mask_mode 2). */
+ * parameters; scratch (double[2*Cin], zeroed by the call) receives scratch[0:Cin] = sum g, scratch[Cin:2Cin] =
+ * sum g*y with g = dx * relu'  (what peclr_bn_bwd_reduce with mask_mode 2 computes in a separate pass).  Follow
+ * with peclr_bn_bwd_apply(mask_mode 2). */
 int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
                                 int k, int stride, const void* bn_y, const float* bn_mean, const float* bn_invstd,
-                                const float* bn_gamma, const float* bn_beta, float* scratch, void* stream);
-/* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x) */
+                                const float* bn_gamma, const float* bn_beta, double* scratch, void* stream);
+/* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x).  The pixel dimension is split over thread blocks; the splits'
+ * partial products go to `workspace` (peclr_conv2d_wgrad_workspace_bytes for the same geometry; may be NULL when
+ * that is 0) and a second kernel adds them to dw in a fixed order. */
+long long peclr_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
 int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
-                       int stride, void* stream);
+                       int stride, void* workspace, long long workspace_bytes, void* stream);
 /* 7x7/stride 2/pad 3 stem (features.0), computed as a 4x4/stride 1 convolution over 2x2 pixel blocks.
  * xpad = [N][H/2+3][W/2+4][16] bf16 from peclr_stem_input (space-to-depth, zero padded),
  * wpack = [64][4][4*16] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */
 int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, int N, int H, int W, double* stat_sum,
                      double* stat_sumsq, void* stream);
 /* dwpack[64][4][64] fp32 += ... ; fold into the (64,3,7,7) gradient with peclr_stem_unpack_grad */
-int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream);
+long long peclr_stem_wgrad_workspace_bytes(int N, int H, int W);
+int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* workspace,
+                     long long workspace_bytes, void* stream);
 
 /* ---- HBM-bound trunk kernels (csrc/bn_act.cu) --------------------------------------------------------
  * Replace nn.BatchNorm2d(train) + ReLU + residual add, MaxPool2d(3,2,1), AdaptiveAvgPool2d(1) of the
@@ -76,15 +85,16 @@ int peclr_bn_apply(const void* y, const double* sum, const double* sumsq, const 
                    float* running_var,
                    float* rmean_out, float* rinvstd_out, float* rrunning_mean, float* rrunning_var, long long M, int C,
                    float eps, float momentum, int relu, void* stream);
-/* scratch[0:C] = sum g, scratch[C:2C] = sum g*y with g = dout * relu'; the ReLU mask is (mask_mode)
+/* scratch (double[2C], zeroed by the call): scratch[0:C] = sum g, scratch[C:2C] = sum g*y with g = dout * relu';
+ * the ReLU mask is (mask_mode)
  * 0: none (dout already masked), 1: the stored activation `mask` > 0, 2: recomputed from y, gamma, beta,
  * 3: `mask` is the bit mask written by peclr_bn_apply. */
 int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
-                        const float* gamma, const float* beta, int mask_mode, float* scratch, long long M, int C,
+                        const float* gamma, const float* beta, int mask_mode, double* scratch, long long M, int C,
                         void* stream);
 /* dy = gamma*invstd*(g - mean g - xhat*mean(g xhat)); optional g_out = g; dbeta += sum g, dgamma += sum g*xhat */
 int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean, const float* invstd,
-                       const float* gamma, const float* beta, int mask_mode, const float* scratch, void* dy,
+                       const float* gamma, const float* beta, int mask_mode, const double* scratch, void* dy,
                        void* g_out, float* dgamma, float* dbeta, long long M, int C, void* stream);
 /* out[N,H/2,W/2,64] = maxpool3x3s2p1(relu(bn(y[N,H,W,64])))   (features.1-3); idx_out (uint8, same shape as
  * out, may be NULL) records the winning window position 0..8 for the backward pass */
@@ -92,21 +102,28 @@ int peclr_stem_bn_relu_pool(const void* y, const double* sum, const double* sums
                             const float* beta, void* out, void* idx_out, float* mean_out, float* invstd_out,
                             float* running_mean, float* running_var, int N, int H, int W, float eps, float momentum,
                             void* stream);
-/* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums (sum g, sum g*y) into scratch[128] */
+/* g_out[N,H,W,64] = relu'(.) * maxpool_backward(dpool) and the BN-backward sums (sum g, sum g*y) into
+ * scratch (double[128]) */
 int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const float* mean, const float* invstd,
-                        const float* gamma, const float* beta, void* g_out, float* scratch, int N, int H, int W,
+                        const float* gamma, const float* beta, void* g_out, double* scratch, int N, int H, int W,
                         void* stream);
 int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
 int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream);
 /* cat(transformed_image1, transformed_image2) (hybrid2_model.py:30-32), fp32 NCHW -> zero-padded bf16
- * space-to-depth batch [2B][H/2+3][W/2+4][16] (channel = dy*6 + dx*3 + c of the 2x2 block; 12..15 zero) */
+ * space-to-depth batch [2B][H/2+3][W/2+4][16] (channel = dy*6 + dx*3 + c of the 2x2 block; 12..15 zero).
+ * x2 == NULL: x1 alone, [B][...] (any batch size: inference, a short last validation batch). */
 int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream);
 
 /* ---- projection head, fp32 (csrc/head.cu); replaces SimCLR.get_projection_head modules
  * (reference src/models/unsupervised/simclr_model.py:20-35) */
-/* C[m,n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]) */
+/* C[m,n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]).  Small GEMMs split K over thread blocks: the
+ * partial tiles go through `workspace` (peclr_sgemm_workspace_bytes; zeroed ONCE by the caller before first use,
+ * it may be shared by GEMMs of different shapes on one stream) and are added in split order by the last block of
+ * each tile.  workspace == NULL: no split (same result up to the summation order, fewer blocks in flight). */
+long long peclr_sgemm_workspace_bytes(int M, int N, int K);
 int peclr_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, long long sam,
-                long long sak, long long sbk, long long sbn, long long ldc, int accumulate, void* stream);
+                long long sak, long long sbk, long long sbn, long long ldc, int accumulate, void* workspace,
+                long long workspace_bytes, void* stream);
 int peclr_bn1d_relu_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean_out,
                         float* invstd_out, float* running_mean, float* running_var, int M, int C, float eps,
                         float momentum, void* stream);
@@ -166,12 +183,12 @@ int peclr_projection_stats(const float* enc, float* out8, int n, int m, int d, v
  * LARSWrapper(torch.optim.Adam).step() as configured by BaseModel.configure_optimizers
  * (src/models/base_model.py:57-104).  seg_begin[num_segs+1] are tensor boundaries, seg_wd the weight
  * decay of each tensor's param group (exclude_from_wt_decay, base_model.py:30-51); chunk_* partition
- * the buffer into blocks of peclr_opt_chunk_elems() that never straddle a tensor; norms is float[2*num_segs]
+ * the buffer into blocks of peclr_opt_chunk_elems() that never straddle a tensor; norms is double[2*num_segs]
  * scratch.  step is the 1-based Adam step.  p_bf16 (optional) receives the updated weights in bf16. */
 int peclr_opt_chunk_elems(void);
 int peclr_lars_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const long long* seg_begin,
                          const float* seg_wd, int num_segs, const int* chunk_seg, const long long* chunk_begin,
-                         int num_chunks, float* norms, float lr, int step, float beta1, float beta2, float adam_eps,
+                         int num_chunks, double* norms, float lr, int step, float beta1, float beta2, float adam_eps,
                          int lars, float eta, int clip, float lars_eps, void* stream);
 int peclr_cast_bf16(const float* src, void* dst, long long n, void* stream);
 /* table: array of {int64 src_off, int64 dst_off, int32 cout, taps, cin, tile_begin}; one launch

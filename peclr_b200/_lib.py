@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PECLR_B200_LIB: load another build of the same ABI (A/B timing of kernel changes); never a fallback
 LIB_PATH = os.environ.get("PECLR_B200_LIB") or os.path.join(_HERE, "libpeclr_b200.so")
 
-ABI_VERSION = 2  # include/peclr_b200.h
+ABI_VERSION = 3  # include/peclr_b200.h
 
 P = c_void_p
 I = c_int
@@ -20,13 +20,14 @@ F = c_float
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "peclr_abi_version": [],
-    "peclr_stat_replicas": [],
     "peclr_conv2d_fprop": [P, P, P, I, I, I, I, I, I, I, P, P, P],
     "peclr_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, P],
     "peclr_conv2d_dgrad_bnreduce": [P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
-    "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P],
+    "peclr_conv2d_wgrad_workspace_bytes": [I, I, I, I, I, I, I],
+    "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P, L, P],
     "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
-    "peclr_stem_wgrad": [P, P, P, I, I, I, P],
+    "peclr_stem_wgrad_workspace_bytes": [I, I, I],
+    "peclr_stem_wgrad": [P, P, P, I, I, I, P, L, P],
     "peclr_bn_apply": [P] * 20 + [L, I, F, F, I, P],
     "peclr_bn_bwd_reduce": [P, P, P, P, P, P, P, I, P, L, I, P],
     "peclr_bn_bwd_apply": [P, P, P, P, P, P, P, I, P, P, P, P, P, L, I, P],
@@ -35,7 +36,8 @@ SIGNATURES = {
     "peclr_avgpool_fwd": [P, P, I, I, I, P],
     "peclr_avgpool_bwd": [P, P, I, I, I, P],
     "peclr_stem_input": [P, P, P, I, I, I, P],
-    "peclr_sgemm": [P, P, P, P, I, I, I, L, L, L, L, L, I, P],
+    "peclr_sgemm_workspace_bytes": [I, I, I],
+    "peclr_sgemm": [P, P, P, P, I, I, I, L, L, L, L, L, I, P, L, P],
     "peclr_bn1d_relu_fwd": [P] * 8 + [I, I, F, F, P],
     "peclr_bn1d_relu_bwd": [P] * 9 + [I, I, P],
     "peclr_colsum_acc": [P, P, I, I, P],
@@ -54,8 +56,10 @@ SIGNATURES = {
     "peclr_stem_pack": [P, P, P],
     "peclr_stem_unpack_grad": [P, P, P],
 }
-_RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong}
-_NO_CHECK = {"peclr_abi_version", "peclr_stat_replicas", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems"}
+_RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong, "peclr_conv2d_wgrad_workspace_bytes": c_longlong,
+             "peclr_stem_wgrad_workspace_bytes": c_longlong, "peclr_sgemm_workspace_bytes": c_longlong}
+_NO_CHECK = {"peclr_abi_version", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems",
+             "peclr_conv2d_wgrad_workspace_bytes", "peclr_stem_wgrad_workspace_bytes", "peclr_sgemm_workspace_bytes"}
 
 _ERRORS = {-1001: "bad argument", -1002: "CUDA driver entry point unavailable", -1003: "TMA tensor-map encoding failed"}
 
@@ -103,6 +107,10 @@ def _kernels_in_call(name, args):
         return 4 if (args[8] == 3 and args[9] == 2) else 1
     if name == "peclr_lars_adam_step":
         return 2 if args[17] else 1
+    if name == "peclr_conv2d_wgrad":  # + the ordered reduction of the pixel splits
+        return 2 if load().peclr_conv2d_wgrad_workspace_bytes(*args[3:10]) > 0 else 1
+    if name == "peclr_stem_wgrad":
+        return 2 if load().peclr_stem_wgrad_workspace_bytes(*args[3:6]) > 0 else 1
     return 1
 
 

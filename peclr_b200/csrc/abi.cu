@@ -1,2 +1,3 @@
 #include "../../include/peclr_b200.h"
-extern "C" int peclr_abi_version(void) { return 2; }  // 2: fp64 BatchNorm sums, space-to-depth stem, accumulator-set scratch
+// 3: reproducible reductions (fp64 accumulators, ordered workspace slabs), workspace arguments of wgrad / sgemm
+extern "C" int peclr_abi_version(void) { return 3; }

@@ -45,25 +45,18 @@ __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
 __device__ __forceinline__ bf16x8 ld8_cached(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
-// mean / inverse std of 8 channels from the sums the convolution epilogue accumulated
-// BN-backward scratch: [kStatReplicas][2C] fp32 accumulator sets, added in order
-__device__ __forceinline__ float stat_total(const float* base, long long stride, int idx) {
-  float t = base[idx];
-#pragma unroll
-  for (int r = 1; r < kStatReplicas; ++r) t += base[r * stride + idx];
-  return t;
-}
-// sum / sumsq: double[C] totals of the conv epilogue.  They are rounded to fp32 at once: fp64 arithmetic is slow on
-// this part (a per-thread fp64 mean / variance cost ~8 us per launch), the fp64 accumulation is only there to make
-// the totals independent of the order in which the CTAs' partial sums arrived.
-__device__ __forceinline__ void bn_coeffs(const double* sum, const double* sumsq, int c0, float inv_m, float eps,
-                                          float (&mean)[8], float (&invstd)[8]) {
+// mean / variance / inverse std of 8 channels from the fp64 sums the convolution epilogue accumulated.  Mean and
+// E[y^2] - mean^2 are formed in fp64 (three double operations per channel): in fp32 the subtraction cancels
+// catastrophically for channels with |mean| >> std.  Only the final values are rounded to fp32.
+__device__ __forceinline__ void bn_coeffs(const double* sum, const double* sumsq, int c0, double inv_m, float eps,
+                                          float (&mean)[8], float (&var)[8], float (&invstd)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float m = (float)sum[c0 + i] * inv_m;
-    const float var = fmaxf((float)sumsq[c0 + i] * inv_m - m * m, 0.f);
-    mean[i] = m;
-    invstd[i] = rsqrtf(var + eps);
+    const double m = sum[c0 + i] * inv_m;
+    const double v = fma(-m, m, sumsq[c0 + i] * inv_m);
+    mean[i] = (float)m;
+    var[i] = fmaxf((float)v, 0.f);
+    invstd[i] = rsqrtf(var[i] + eps);
   }
 }
 
@@ -109,16 +102,16 @@ struct BnApplyArgs {
   int contig;  // 1: each block walks one contiguous row range (DRAM locality) instead of a grid-strided one
 };
 
-__device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const float (&invstd)[8], int c0, long long M,
-                                               float eps, float momentum, float* mean_out, float* invstd_out,
-                                               float* running_mean, float* running_var) {
+__device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const float (&var)[8],
+                                               const float (&invstd)[8], int c0, long long M, float momentum,
+                                               float* mean_out, float* invstd_out, float* running_mean,
+                                               float* running_var) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     mean_out[c0 + i] = mean[i];
     invstd_out[c0 + i] = invstd[i];
     if (running_mean) {
-      const float var = 1.f / (invstd[i] * invstd[i]) - eps;
-      const float unbiased = M > 1 ? var * (float)((double)M / (double)(M - 1)) : var;
+      const float unbiased = M > 1 ? var[i] * (float)((double)M / (double)(M - 1)) : var[i];
       running_mean[c0 + i] = (1.f - momentum) * running_mean[c0 + i] + momentum * mean[i];
       running_var[c0 + i] = (1.f - momentum) * running_var[c0 + i] + momentum * unbiased;
     }
@@ -132,9 +125,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const int cg = threadIdx.x % tpr;
   const int roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
-  const float inv_m = 1.f / (float)a.M;
-  float mean[8], invstd[8], scale[8], shift[8];
-  bn_coeffs(a.sum, a.sumsq, c0, inv_m, a.eps, mean, invstd);
+  const double inv_m = 1.0 / (double)a.M;
+  float mean[8], var[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(a.sum, a.sumsq, c0, inv_m, a.eps, mean, var, invstd);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     scale[i] = a.gamma[c0 + i] * invstd[i];
@@ -144,22 +137,22 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const bool has_res = a.res != nullptr;
   const bool res_bn = has_res && a.rsum != nullptr;
   if (res_bn) {
-    float rmean[8], rinvstd[8];
-    bn_coeffs(a.rsum, a.rsumsq, c0, inv_m, a.eps, rmean, rinvstd);
+    float rmean[8], rvar[8], rinvstd[8];
+    bn_coeffs(a.rsum, a.rsumsq, c0, inv_m, a.eps, rmean, rvar, rinvstd);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       rscale[i] = a.rgamma[c0 + i] * rinvstd[i];
       rshift[i] = a.rbeta[c0 + i] - rmean[i] * rscale[i];
     }
     if (blockIdx.x == 0 && roff == 0)
-      bn_bookkeeping(rmean, rinvstd, c0, a.M, a.eps, a.momentum, a.rmean_out, a.rinvstd_out, a.rrunning_mean,
+      bn_bookkeeping(rmean, rvar, rinvstd, c0, a.M, a.momentum, a.rmean_out, a.rinvstd_out, a.rrunning_mean,
                      a.rrunning_var);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) rscale[i] = 1.f, rshift[i] = 0.f;
   }
   if (blockIdx.x == 0 && roff == 0)
-    bn_bookkeeping(mean, invstd, c0, a.M, a.eps, a.momentum, a.mean_out, a.invstd_out, a.running_mean, a.running_var);
+    bn_bookkeeping(mean, var, invstd, c0, a.M, a.momentum, a.mean_out, a.invstd_out, a.running_mean, a.running_var);
 
   const RowWalk rw = row_walk<kRows>(a.M, rows_per_block, roff, a.contig);
   for (long long r = rw.r0; r < rw.rend; r += rw.rstep) {
@@ -209,7 +202,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
 struct BnBwdArgs {
   const __nv_bfloat16 *dout, *mask, *y;
   const float *mean, *invstd, *gamma, *beta;
-  float* scratch;          // [kStatReplicas][2C]: sum g, sum g*y
+  double* scratch;         // [2C] fp64 accumulators: sum g, sum g*y (one partial per block, fixed order inside)
   __nv_bfloat16 *dy, *g_out;
   float *dgamma, *dbeta;
   long long M;
@@ -219,7 +212,8 @@ struct BnBwdArgs {
 
 // Pass 1 (kApply = false) accumulates sum g and sum g*y per channel; pass 2 folds everything into three
 // per-channel constants: dy = A*g + B*y + C with A = gamma*invstd, B = -A*invstd*k3, C = -A*(k2 - k3*invstd*mean),
-// k2 = mean(g), k3 = mean(g*xhat) = invstd*(mean(g*y) - mean*mean(g)).  Few live registers -> 3-4 blocks per SM.
+// k2 = mean(g), k3 = mean(g*xhat) = invstd*(mean(g*y) - mean*mean(g)) -- that difference is formed in fp64 from the
+// fp64 totals (it cancels like a variance).  Few live registers -> 3-4 blocks per SM.
 template <bool kApply, int kMask, int kRows>
 __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwdArgs a) {
   __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][kApply ? 1 : 9];
@@ -239,9 +233,9 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
     }
     s[i] = d[i] = 0.f;
     if (kApply) {
-      const float sg = stat_total(a.scratch, 2 * a.C, c0 + i);
-      const float sgy = stat_total(a.scratch, 2 * a.C, a.C + c0 + i);
-      const float sgx = is * (sgy - mu * sg);
+      const double sgd = a.scratch[c0 + i], sgyd = a.scratch[a.C + c0 + i];
+      const float sg = (float)sgd;
+      const float sgx = (float)((double)is * fma(-(double)mu, sgd, sgyd));
       const float k2 = sg * inv_m, k3 = sgx * inv_m;
       ka[i] = gm * is;
       kb[i] = -ka[i] * is * k3;
@@ -310,9 +304,8 @@ __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwd
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float* set = a.scratch + (size_t)(blockIdx.x % kStatReplicas) * 2 * a.C;
-        red_add_f32(set + c0 + i, s[i]);
-        red_add_f32(set + a.C + c0 + i, d[i]);
+        red_add_f64(a.scratch + c0 + i, (double)s[i]);
+        red_add_f64(a.scratch + a.C + c0 + i, (double)d[i]);
       }
     }
   }
@@ -383,15 +376,15 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
   const long long M = (long long)N * H * W;
-  float mean[8], invstd[8], scale[8], shift[8];
-  bn_coeffs(sum, sumsq, c0, 1.f / (float)M, eps, mean, invstd);
+  float mean[8], var[8], invstd[8], scale[8], shift[8];
+  bn_coeffs(sum, sumsq, c0, 1.0 / (double)M, eps, mean, var, invstd);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     scale[i] = gamma[c0 + i] * invstd[i];
     shift[i] = beta[c0 + i] - mean[i] * scale[i];
   }
   if (blockIdx.x == 0 && roff == 0)
-    bn_bookkeeping(mean, invstd, c0, M, eps, momentum, mean_out, invstd_out, running_mean, running_var);
+    bn_bookkeeping(mean, var, invstd, c0, M, momentum, mean_out, invstd_out, running_mean, running_var);
   uint32_t flip[4];  // sign-bit flips that make "larger raw value" mean "larger activation"
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -482,7 +475,7 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
-                                                            __nv_bfloat16* __restrict__ g_out, float* scratch, int N,
+                                                            __nv_bfloat16* __restrict__ g_out, double* scratch, int N,
                                                             int H, int W) {
   __shared__ float red[2][256][9];
   const int C = 64, tpr = 8;
@@ -555,9 +548,8 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float* set = scratch + (size_t)(blockIdx.x % kStatReplicas) * 2 * C;
-      red_add_f32(set + c0 + i, s[i]);
-      red_add_f32(set + C + c0 + i, d[i]);
+      red_add_f64(scratch + c0 + i, (double)s[i]);
+      red_add_f64(scratch + C + c0 + i, (double)d[i]);
     }
   }
 }
@@ -609,15 +601,17 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 // in channel order (dy, dx, c) -> dy * 6 + dx * 3 + c; channels 12..15 and the border are zero.  The 7x7 / stride 2
 // stem then is a 4 x 4 / stride 1 convolution over 16-channel pixels (csrc/conv_ops.cu, stem_views).
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
-                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+                                                         __nv_bfloat16* __restrict__ out, int B1, int Ntot, int H,
+                                                         int W) {
   const int Hs = H / 2 + 3, Ws = W / 2 + 4;
   const size_t cs = (size_t)H * W;
   // one block iteration = one padded row (n, yp); threads walk the padded blocks (coalesced float2 plane reads)
-  for (int row = blockIdx.x; row < 2 * B * Hs; row += gridDim.x) {
+  for (int row = blockIdx.x; row < Ntot * Hs; row += gridDim.x) {
     const int n = row / Hs, yp = row - n * Hs;
     const int y = yp - 2;
     const bool row_ok = y >= 0 && y < H / 2;
-    const float* src = (n < B ? x1 + (size_t)n * 3 * cs : x2 + (size_t)(n - B) * 3 * cs) +
+    // (images B1 .. 2 B1 - 1 come from x2; with x2 == NULL the batch is x1 alone)
+    const float* src = (n < B1 ? x1 + (size_t)n * 3 * cs : x2 + (size_t)(n - B1) * 3 * cs) +
                        (size_t)(row_ok ? 2 * y : 0) * W;
     uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)row * Ws * 2;
     for (int xp = threadIdx.x; xp < Ws; xp += 256) {
@@ -702,9 +696,9 @@ extern "C" int peclr_bn_apply(const void* y, const double* sum, const double* su
 
 extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const void* y, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, int mask_mode,
-                                   float* scratch, long long M, int C, void* stream) {
+                                   double* scratch, long long M, int C, void* stream) {
   if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * C * sizeof(float), (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * C * sizeof(double), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean, invstd, gamma, beta, scratch,
               nullptr,           nullptr,           nullptr,        nullptr, M,    C,     mask_mode, elt_contig()};
@@ -715,10 +709,10 @@ extern "C" int peclr_bn_bwd_reduce(const void* dout, const void* mask, const voi
 
 extern "C" int peclr_bn_bwd_apply(const void* dout, const void* mask, const void* y, const float* mean,
                                   const float* invstd, const float* gamma, const float* beta, int mask_mode,
-                                  const float* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
+                                  const double* scratch, void* dy, void* g_out, float* dgamma, float* dbeta,
                                   long long M, int C, void* stream) {
   if (bad_channels(C) || mask_mode < 0 || mask_mode > 3 || ((mask_mode & 1) && !mask)) return -1001;
-  BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<float*>(scratch),
+  BnBwdArgs a{(const bf16*)dout, (const bf16*)mask, (const bf16*)y, mean,   invstd, gamma, beta, const_cast<double*>(scratch),
               (bf16*)dy,         (bf16*)g_out,      dgamma,         dbeta,  M,      C,     mask_mode, elt_contig()};
   const int rows_per_block = 256 / (C / 8);
   launch_bn_bwd<true>(a, grid_for(M, rows_per_block * elt_rows()), (cudaStream_t)stream);
@@ -738,9 +732,9 @@ extern "C" int peclr_stem_bn_relu_pool(const void* y, const double* sum, const d
 
 extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const void* y, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, void* g_out,
-                                   float* scratch, int N, int H, int W, void* stream) {
+                                   double* scratch, int N, int H, int W, void* stream) {
   if ((H & 1) || (W & 1) || !idx) return -1001;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * 64 * sizeof(float), (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * 64 * sizeof(double), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
   stem_pool_bwd_kernel<<<grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H,
@@ -763,8 +757,9 @@ extern "C" int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int
 }
 
 extern "C" int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream) {
-  if ((H & 1) || (W & 1)) return -1001;
-  stem_input_kernel<<<grid_for((long long)2 * B * (H / 2 + 3), 1, 8), 256, 0, (cudaStream_t)stream>>>(
-      x1, x2, (bf16*)out, B, H, W);
+  if ((H & 1) || (W & 1) || B < 1 || !x1) return -1001;
+  const int ntot = x2 ? 2 * B : B;  // x2 == NULL: a plain batch of B images (inference / odd batch sizes)
+  stem_input_kernel<<<grid_for((long long)ntot * (H / 2 + 3), 1, 8), 256, 0, (cudaStream_t)stream>>>(
+      x1, x2, (bf16*)out, B, ntot, H, W);
   return last_error();
 }

@@ -74,8 +74,6 @@ static void halo_taps_3x3(TapTable* taps, bool dgrad, int kc) {
 
 using namespace peclr;
 
-extern "C" int peclr_stat_replicas(void) { return kStatReplicas; }
-
 extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
                                   int stride, double* stat_sum, double* stat_sumsq, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -88,25 +86,25 @@ extern "C" int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, 
     memset(&taps, 0, sizeof(taps));
     views[0] = flat_view(x, (int64_t)N * H * W, Cin);
     View4 d = flat_view(y, (int64_t)N * H * W, Cout);
-    return conv_gemm_launch(views, 1, w, Cin, Cout, d, taps, 1, Cin / 64, stat_sum, stat_sumsq, 0, 0, st);
+    return conv_gemm_launch(views, 1, w, Cin, Cout, d, taps, 1, Cin / 64, stat_sum, stat_sumsq, 0, st);
   }
   const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
   if (nv < 0) return nv;
   View4 d = nhwc_view(y, N, Ho, Wo, Cout);
   if (k == 3 && stride == 1 && halo_ok(Cout, (int64_t)N * Ho * Wo)) {
     halo_taps_3x3(&taps, false, Cin);
-    return conv_gemm_launch(views, 1, w, (int64_t)9 * Cin, Cout, d, taps, 3, Cin / 64, stat_sum, stat_sumsq, 0, 0, st,
+    return conv_gemm_launch(views, 1, w, (int64_t)9 * Cin, Cout, d, taps, 3, Cin / 64, stat_sum, stat_sumsq, 0, st,
                             nullptr, 3, 3 * Cin);
   }
   return conv_gemm_launch(views, nv, w, (int64_t)num_taps * Cin, Cout, d, taps, num_taps, Cin / 64, stat_sum,
-                          stat_sumsq, 0, 0, st);
+                          stat_sumsq, 0, st);
 }
 
 // dgrad, optionally with the BatchNorm-backward reduction of the BN (+ReLU) in front of this convolution fused
 // into the epilogue (bn_y = that BN's input, same shape as dx; scratch[0:Cin] += sum g, scratch[Cin:2Cin] += sum g*y)
 static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                       int stride, int accumulate, const void* bn_y, const float* bn_mean, const float* bn_invstd,
-                      const float* bn_gamma, const float* bn_beta, float* scratch, cudaStream_t st) {
+                      const float* bn_gamma, const float* bn_beta, double* scratch, cudaStream_t st) {
   if (Cin % 64 || Cout % 64 || (k != 1 && k != 3)) return PECLR_ERR_ARG;
   if (bn_y && (accumulate || !scratch || Cin > 2048)) return PECLR_ERR_ARG;
   const int Ho = H / stride, Wo = W / stride;
@@ -114,10 +112,10 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
   memset(&taps, 0, sizeof(taps));
   View4 a;
   const int64_t ktot = (int64_t)k * k * Cout;
-  float* s_sum = bn_y ? scratch : nullptr;
-  float* s_sq = bn_y ? scratch + Cin : nullptr;
+  double* s_sum = bn_y ? scratch : nullptr;
+  double* s_sq = bn_y ? scratch + Cin : nullptr;
   if (bn_y) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)kStatReplicas * 2 * Cin * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * Cin * sizeof(double), st);
     if (e != cudaSuccess) return -(int)e;
   }
   // the y tile of a launch sits at the same offset from bn_y as the output view does from dx
@@ -132,7 +130,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
     if (k == 1) {
       a = flat_view(dy, (int64_t)N * H * W, Cout);
       View4 d = flat_view(dx, (int64_t)N * H * W, Cin);
-      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, s_sum, s_sq, accumulate, st,
                               bnr_for(d, &br));
     }
     a = nhwc_view(dy, N, H, W, Cout);
@@ -146,10 +144,10 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
     View4 d = nhwc_view(dx, N, H, W, Cin);
     if (halo_ok(Cin, (int64_t)N * H * W)) {
       halo_taps_3x3(&taps, true, Cout);
-      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 3, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
+      return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 3, Cout / 64, s_sum, s_sq, accumulate, st,
                               bnr_for(d, &br), 3, -3 * Cout);
     }
-    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 9, Cout / 64, s_sum, s_sq, accumulate, st,
                             bnr_for(d, &br));
   }
   if (stride != 2 || (H & 1) || (W & 1)) return PECLR_ERR_ARG;
@@ -162,7 +160,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
       if (e != cudaSuccess) return -(int)e;
     }
     View4 d = parity_view(dx, N, H, W, Cin, 0, 0);
-    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, 0, accumulate, st);
+    return conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, 1, Cout / 64, nullptr, nullptr, accumulate, st);
   }
   // 3x3 stride 2: one launch per parity class of the input pixel; taps r with (ph + 1 - r) even
   for (int ph = 0; ph < 2; ++ph)
@@ -180,7 +178,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
         }
       }
       View4 d = parity_view(dx, N, H, W, Cin, ph, pw);
-      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, s_sum, s_sq, 2 * Cin, accumulate, st,
+      int rc = conv_gemm_launch(&a, 1, wt, ktot, Cin, d, taps, t, Cout / 64, s_sum, s_sq, accumulate, st,
                                 bnr_for(d, &br));
       if (rc) return rc;
     }
@@ -196,30 +194,47 @@ extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int 
 extern "C" int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
                                            int Cout, int k, int stride, const void* bn_y, const float* bn_mean,
                                            const float* bn_invstd, const float* bn_gamma, const float* bn_beta,
-                                           float* scratch, void* stream) {
+                                           double* scratch, void* stream) {
   if (!bn_y || !bn_mean || !bn_invstd || !bn_gamma || !bn_beta) return PECLR_ERR_ARG;
   return dgrad_impl(dy, wt, dx, N, H, W, Cin, Cout, k, stride, 0, bn_y, bn_mean, bn_invstd, bn_gamma, bn_beta, scratch,
                     static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
-                                  int k, int stride, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// views + tap table of a weight-gradient launch (shared by the workspace query and the launch)
+static int wgrad_geometry(const void* x, const void* dy, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                          View4* views, TapTable* taps, int* num_taps, View4* d) {
   if (Cin % 64 || Cout % 64) return PECLR_ERR_ARG;
   const int Ho = H / stride, Wo = W / stride;
+  if (k == 1 && stride == 1) {
+    memset(taps, 0, sizeof(*taps));
+    views[0] = flat_view(x, (int64_t)N * H * W, Cin);
+    *d = flat_view(dy, (int64_t)N * H * W, Cout);
+    *num_taps = 1;
+    return 1;
+  }
+  const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, taps, num_taps);
+  *d = nhwc_view(dy, N, Ho, Wo, Cout);
+  return nv;
+}
+
+extern "C" long long peclr_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride) {
   TapTable taps;
   int num_taps = 0;
-  View4 views[kMaxViews];
-  if (k == 1 && stride == 1) {
-    memset(&taps, 0, sizeof(taps));
-    views[0] = flat_view(x, (int64_t)N * H * W, Cin);
-    View4 d = flat_view(dy, (int64_t)N * H * W, Cout);
-    return conv_wgrad_launch(views, 1, d, taps, 1, Cin, Cout, dw, st);
-  }
-  const int nv = input_side(x, N, H, W, Cin, k, stride, Cin, views, &taps, &num_taps);
+  View4 views[kMaxViews], d;
+  const int nv = wgrad_geometry(nullptr, nullptr, N, H, W, Cin, Cout, k, stride, views, &taps, &num_taps, &d);
   if (nv < 0) return nv;
-  View4 d = nhwc_view(dy, N, Ho, Wo, Cout);
-  return conv_wgrad_launch(views, nv, d, taps, num_taps, Cin, Cout, dw, st);
+  return conv_wgrad_workspace_bytes(d, num_taps, Cin, Cout);
+}
+
+extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                                  int k, int stride, void* workspace, long long workspace_bytes, void* stream) {
+  TapTable taps;
+  int num_taps = 0;
+  View4 views[kMaxViews], d;
+  const int nv = wgrad_geometry(x, dy, N, H, W, Cin, Cout, k, stride, views, &taps, &num_taps, &d);
+  if (nv < 0) return nv;
+  return conv_wgrad_launch(views, nv, d, taps, num_taps, Cin, Cout, dw, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 // ---- 7x7 / stride 2 / pad 3 stem as a 4x4 / stride 1 convolution on the space-to-depth image ----------------
@@ -249,18 +264,26 @@ extern "C" int peclr_stem_fprop(const void* xpad, const void* wpack, void* y, in
   View4 d = View4{y, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
   if (halo_ok(64, (int64_t)N * (H / 2) * (W / 2))) {  // the four filter rows as one tap group
     taps.dh[0] = 0, taps.dw[0] = 0, taps.view[0] = 0, taps.koff[0] = 0;
-    return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 1, 1, stat_sum, stat_sumsq, 0, 0,
+    return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 1, 1, stat_sum, stat_sumsq, 0,
                             static_cast<cudaStream_t>(stream), nullptr, 4, 64);
   }
-  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0, 0,
+  return conv_gemm_launch(views, 1, wpack, 4 * 64, 64, d, taps, 4, 1, stat_sum, stat_sumsq, 0,
                           static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* stream) {
+extern "C" long long peclr_stem_wgrad_workspace_bytes(int N, int H, int W) {
+  if ((H & 1) || (W & 1)) return PECLR_ERR_ARG;
+  View4 d = View4{nullptr, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
+  return conv_wgrad_workspace_bytes(d, 4, 64, 64);
+}
+
+extern "C" int peclr_stem_wgrad(const void* xpad, const void* dy, float* dwpack, int N, int H, int W, void* workspace,
+                                long long workspace_bytes, void* stream) {
   if ((H & 1) || (W & 1)) return PECLR_ERR_ARG;
   View4 views[kMaxViews];
   TapTable taps;
   stem_views(xpad, N, H, W, views, &taps);
   View4 d = View4{dy, 64, W / 2, H / 2, N, 64, (int64_t)(W / 2) * 64, (int64_t)(H / 2) * (W / 2) * 64};
-  return conv_wgrad_launch(views, 1, d, taps, 4, 64, 64, dwpack, static_cast<cudaStream_t>(stream));
+  return conv_wgrad_launch(views, 1, d, taps, 4, 64, 64, dwpack, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }

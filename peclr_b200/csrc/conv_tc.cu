@@ -20,7 +20,8 @@
 //       both operands are loaded exactly as above ([pixels][64 channels] boxes) and consumed as
 //       MN-major UMMA operands (contraction over pixels); M = 128 input channels, N = BN output
 //       channels, up to 512/BN taps accumulate side by side in TMEM; split over pixel ranges across
-//       CTAs and reduced with fp32 red.global.add.
+//       CTAs: every split writes its fp32 partial to a workspace slab and wgrad_reduce_kernel adds the slabs
+//       to dW in a fixed order (no atomics: the weight gradients are bit-reproducible run to run).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), then the epilogue warps (8 in the
 // fprop/dgrad kernel: two per TMEM lane quarter, splitting the columns; 4 in the wgrad kernel).
@@ -45,13 +46,11 @@ struct GemmParams {
   int log_wb, log_wbhb;
   int d_w, d_h, d_n;
   int cout;
-  // per-channel statistics of the stored tile values, accumulated across CTAs.  Forward (BatchNorm sums): fp64
-  // accumulators (see red_add_f64).  Fused BN-backward reduction (stat_f32): fp32 accumulators in kStatReplicas
-  // sets stat_stride elements apart, CTA b adds into set b % kStatReplicas.
-  void* stat_sum;
-  void* stat_sumsq;
-  long long stat_stride;
-  int stat_f32;
+  // per-channel statistics of the stored tile values (forward: BatchNorm sums; fused BN-backward reduction: sum g,
+  // sum g*y).  Every CTA accumulates its tiles in a fixed order in shared memory and adds ONE fp64 partial per
+  // channel to these accumulators (see red_add_f64): the totals do not depend on the arrival order of the CTAs.
+  double* stat_sum;
+  double* stat_sumsq;
   int reduce_add;
   // fused BatchNorm-backward reduction (dgrad feeding an inner BN + ReLU): with y = that BN's input tile,
   // g = D * [fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0]; stat_sum += sum g, stat_sumsq += sum g*y
@@ -64,7 +63,8 @@ struct GemmParams {
   // multiple of the 1024-byte swizzle atom).  Tap t's weights sit halo_kstep columns after tap t - 1's.
   int halo_taps, halo_kstep;
   int halo_a_bytes, halo_stage_a, halo_stages;
-  int stat_copies;  // 512 / BN private copies of the per-CTA statistics (one owner thread per address), or 1 (atomics)
+  int stat_copies;  // 512 / BN private copies of the per-CTA statistics (one owner thread per address), or 1 (the
+                    // row groups then take turns on the single copy, in a fixed order)
 };
 
 // CTAS == 2: the two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2).  Each CTA stages its own
@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ybar + 2);
   // per-CTA statistics, one private copy per row group ([512/BN][2][cout]): every address has exactly one owner
-  // thread, so the per-tile accumulation is a plain read-modify-write (shared fp32 atomics are CAS loops).  When
-  // the copies do not fit next to the pipeline stages (stat_copies == 1) the threads fall back to shared atomics.
+  // thread, so the per-tile accumulation is a plain read-modify-write in a fixed order (reproducible; shared fp32
+  // atomics are CAS loops and would add in arrival order).  When the copies do not fit next to the pipeline stages
+  // (stat_copies == 1) the row groups take turns on one copy, separated by named barriers.
   float* sStat = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -372,11 +373,16 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
           *mine_s = as, *mine_q = aq;
         } else {
-          const uint32_t ss = smem_u32(sStat) + (nt * BN + col) * 4;
-          red_shared_add_f32(ss, s0 + s2);
-          red_shared_add_f32(ss + 4, s1 + s3);
-          red_shared_add_f32(ss + p.cout * 4, q0 + q2);
-          red_shared_add_f32(ss + p.cout * 4 + 4, q1 + q3);
+          for (int g = 0; g < kRowGroups; ++g) {  // fixed order: row group 0 first
+            if (rg == g) {
+              float2* mine_s = reinterpret_cast<float2*>(sStat + nt * BN + col);
+              float2* mine_q = reinterpret_cast<float2*>(sStat + p.cout + nt * BN + col);
+              float2 as = *mine_s, aq = *mine_q;
+              as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
+              *mine_s = as, *mine_q = aq;
+            }
+            named_bar_sync(3, 256);
+          }
         }
         if (p.bn_reduce) {  // every thread is done with the y tile: hand the buffer back to the producer
           named_bar_sync(2, 256);
@@ -391,14 +397,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         float s = 0.f, qq = 0.f;
         for (int g = 0; g < p.stat_copies; ++g) s += sStat[g * 2 * p.cout + i], qq += sStat[g * 2 * p.cout + p.cout + i];
         if (s != 0.f || qq != 0.f) {
-          if (p.stat_f32) {
-            const long long rep = (long long)(blockIdx.x % kStatReplicas) * p.stat_stride;
-            red_add_f32(static_cast<float*>(p.stat_sum) + rep + i, s);
-            red_add_f32(static_cast<float*>(p.stat_sumsq) + rep + i, qq);
-          } else {
-            red_add_f64(static_cast<double*>(p.stat_sum) + i, (double)s);
-            red_add_f64(static_cast<double*>(p.stat_sumsq) + i, (double)qq);
-          }
+          red_add_f64(p.stat_sum + i, (double)s);
+          red_add_f64(p.stat_sumsq + i, (double)qq);
         }
       }
     }
@@ -427,6 +427,8 @@ struct WgradParams {
   int cin, a_boxes;
   int64_t ld_co;  // elements between consecutive output channels in dW ( = taps * cin )
   float* dw;
+  float* partial;          // ksplit > 1: [ksplit][cout * taps * cin] slabs in dW's layout (plain stores)
+  int64_t partial_stride;  // elements per slab
 };
 
 template <int BN>
@@ -561,7 +563,8 @@ __global__ void __maxnreg__(80) conv_wgrad_kernel(const __grid_constant__ WgradP
         ci = (q & 1) * 32 + lane;
         if (tap >= p.num_taps) ci = p.cin;  // nothing to write
       }
-      float* out = p.dw + static_cast<int64_t>(tap) * p.cin + ci;
+      // one pixel split: read-modify-write of dW by its only writer; several: this split's slab of the workspace
+      float* out = (p.ksplit > 1 ? p.partial + ks * p.partial_stride : p.dw) + static_cast<int64_t>(tap) * p.cin + ci;
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t r[32];
@@ -569,10 +572,18 @@ __global__ void __maxnreg__(80) conv_wgrad_kernel(const __grid_constant__ WgradP
         tmem_ld_wait();
         if (ci < p.cin) {
           float* o = out + static_cast<int64_t>(nt * BN + chunk * 32) * p.ld_co;
+          if (p.ksplit > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            red_add_f32(o, __uint_as_float(r[j]));
-            o += p.ld_co;
+            for (int j = 0; j < 32; ++j) {
+              *o = __uint_as_float(r[j]);
+              o += p.ld_co;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              *o += __uint_as_float(r[j]);
+              o += p.ld_co;
+            }
           }
         }
       }
@@ -583,6 +594,20 @@ __global__ void __maxnreg__(80) conv_wgrad_kernel(const __grid_constant__ WgradP
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// dW += sum over the pixel splits' slabs, in slab order (fixed summation order -> reproducible weight gradients)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partial, float4* dw, int64_t n4,
+                                                           int ksplit) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 acc = dw[i];
+#pragma unroll 4
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const float4 v = __ldcs(partial + (int64_t)ks * n4 + i);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    dw[i] = acc;
   }
 }
 
@@ -758,9 +783,9 @@ bool conv_halo_enabled() {
 }
 
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
-                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
-                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr,
-                     int halo_taps, int halo_kstep) {
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, double* stat_sum,
+                     double* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr, int halo_taps,
+                     int halo_kstep) {
   if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
   if (nout % 64 != 0 || ktot % 64 != 0 || d_view.c != nout) return PECLR_ERR_ARG;
   if (stat_sum && nout > 2048) return PECLR_ERR_ARG;
@@ -816,8 +841,6 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.cout = (int)nout;
   p.stat_sum = stat_sum;
   p.stat_sumsq = stat_sumsq;
-  p.stat_stride = stat_stride;
-  p.stat_f32 = bnr != nullptr;  // forward BatchNorm sums are fp64; the fused BN-backward reduction uses fp32 sets
   p.reduce_add = reduce_add;
   const bool stats = stat_sum != nullptr;
   if (halo) {
@@ -847,21 +870,13 @@ static int launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   return e == cudaSuccess ? 0 : -(int)e;
 }
 
-int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
-                      int cin, int cout, float* dw, cudaStream_t stream) {
-  if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
-  if (cin % 64 != 0 || cout % 64 != 0 || dy_view.c != cout) return PECLR_ERR_ARG;
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
+// Tiling of a weight-gradient launch (everything but the tensor maps): shared by the launch and the workspace query.
+static int wgrad_plan(const View4& dy_view, int num_taps, int cin, int cout, WgradParams* pp, int* bn_out) {
+  WgradParams& p = *pp;
   int bw = 1, bh = 1, bn = 1;
   choose_box((int)dy_view.w, (int)dy_view.h, (int)dy_view.n, 64, &bw, &bh, &bn);
-  int rc;
-  for (int i = 0; i < kMaxViews; ++i)
-    if ((rc = encode_view(&p.x_maps[i], x_views[i < num_views ? i : 0], bw, bh, bn))) return rc;
-  if ((rc = encode_view(&p.dy_map, dy_view, bw, bh, bn))) return rc;
   // multi-tap filters keep several taps' accumulators side by side in TMEM (dY is loaded once per group)
   const int BN = num_taps > 1 ? (cout % 128 == 0 ? 128 : 64) : (cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64));
-  p.taps = taps;
   p.num_taps = num_taps;
   p.taps_per_unit = num_taps == 9 ? 3 : (num_taps < 4 ? num_taps : 4);  // G * BN <= 512 columns, >= 2 smem stages
   p.tap_groups = (num_taps + p.taps_per_unit - 1) / p.taps_per_unit;
@@ -899,13 +914,53 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   const int max_split = (chunks + 7) / 8;  // at least 8 pixel chunks (512 pixels) per unit
   if (ksplit > max_split) ksplit = max_split;
   if (ksplit < 1) ksplit = 1;
+  // no empty pixel ranges: every split writes its whole slab, the reduction reads all of them
+  const int per = (chunks + ksplit - 1) / ksplit;
+  ksplit = (chunks + per - 1) / per;
   p.ksplit = ksplit;
   p.cin = cin;
   p.ld_co = (int64_t)num_taps * cin;
+  p.partial_stride = (int64_t)cout * num_taps * cin;
+  *bn_out = BN;
+  return 0;
+}
+
+long long conv_wgrad_workspace_bytes(const View4& dy_view, int num_taps, int cin, int cout) {
+  if (num_taps < 1 || num_taps > kMaxTaps || cin % 64 != 0 || cout % 64 != 0) return PECLR_ERR_ARG;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int BN = 0;
+  wgrad_plan(dy_view, num_taps, cin, cout, &p, &BN);
+  return p.ksplit > 1 ? (long long)p.ksplit * p.partial_stride * 4 : 0;
+}
+
+int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
+                      int cin, int cout, float* dw, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  if (num_views < 1 || num_views > kMaxViews || num_taps < 1 || num_taps > kMaxTaps) return PECLR_ERR_ARG;
+  if (cin % 64 != 0 || cout % 64 != 0 || dy_view.c != cout) return PECLR_ERR_ARG;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int BN = 0;
+  wgrad_plan(dy_view, num_taps, cin, cout, &p, &BN);
+  if (p.ksplit > 1 && (!workspace || workspace_bytes < (long long)p.ksplit * p.partial_stride * 4)) return PECLR_ERR_ARG;
+  int rc;
+  for (int i = 0; i < kMaxViews; ++i)
+    if ((rc = encode_view(&p.x_maps[i], x_views[i < num_views ? i : 0], p.Wb, p.Hb, p.Nb))) return rc;
+  if ((rc = encode_view(&p.dy_map, dy_view, p.Wb, p.Hb, p.Nb))) return rc;
+  p.taps = taps;
   p.dw = dw;
-  if (BN == 256) return launch_wgrad_t<256>(p, stream);
-  if (BN == 128) return launch_wgrad_t<128>(p, stream);
-  return launch_wgrad_t<64>(p, stream);
+  p.partial = static_cast<float*>(workspace);
+  if (BN == 256) rc = launch_wgrad_t<256>(p, stream);
+  else if (BN == 128) rc = launch_wgrad_t<128>(p, stream);
+  else rc = launch_wgrad_t<64>(p, stream);
+  if (rc || p.ksplit == 1) return rc;
+  const int64_t n4 = p.partial_stride / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(p.partial),
+                                                       reinterpret_cast<float4*>(dw), n4, p.ksplit);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
 }
 
 }  // namespace peclr

@@ -11,13 +11,9 @@
 
 namespace peclr {
 
-// The BN-backward sums (scratch buffers) are kept as kStatReplicas fp32 accumulator sets: block b adds its partial
-// into set b % kStatReplicas, the consumer adds the sets in order.  Replication divides the number of atomics
-// serialised on one address (the tail of the reduction kernels; measured 4-12 us per launch).  The forward
-// statistics of the conv epilogue are one fp64 set: fp64 makes the totals independent of the order in which the
-// CTAs' partials arrive (the forward pass, hence the loss, is reproducible run to run); the backward sums stay fp32
-// because fp64 arithmetic in the consumers' per-thread prologues is slow on this part (+0.4 ms per step measured).
-constexpr int kStatReplicas = 4;
+// Cross-CTA reductions are reproducible by construction: per-channel statistics (forward BatchNorm sums, BN-backward
+// sums) are added as ONE fp64 partial per CTA (each computed in a fixed order) into fp64 accumulators, whose totals
+// do not depend on the arrival order; weight-gradient pixel splits go through workspace slabs added in slab order.
 constexpr int kMaxViews = 4;
 constexpr int kMaxTaps = 16;
 
@@ -48,15 +44,18 @@ struct BnReduce {
 
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.
 int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t ktot, int64_t nout,
-                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, void* stat_sum,
-                     void* stat_sumsq, int64_t stat_stride, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr,
+                     const View4& d_view, const TapTable& taps, int num_taps, int c_chunks, double* stat_sum,
+                     double* stat_sumsq, int reduce_add, cudaStream_t stream, const BnReduce* bnr = nullptr,
                      int halo_taps = 0, int halo_kstep = 0);
 // halo_taps > 1: every tap-table entry is a group of halo_taps taps with dh = entry.dh + t (t = 0 .. halo_taps - 1),
 // whose weights are halo_kstep K-columns apart; the kernel loads one tall input box per group (see conv_tc.cu).
 bool conv_halo_enabled();
 
-// dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin)
+// dW[n, tap, c] += sum_pix dY[pix, n] * X_view[pix + tap, c]   (fp32, ld between n = num_taps * cin).  The pixel
+// dimension is split over CTAs; with more than one split the partials go through `workspace`
+// (conv_wgrad_workspace_bytes) and are added to dW in a fixed order by a second kernel.
+long long conv_wgrad_workspace_bytes(const View4& dy_view, int num_taps, int cin, int cout);
 int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
-                      int cin, int cout, float* dw, cudaStream_t stream);
+                      int cin, int cout, float* dw, void* workspace, long long workspace_bytes, cudaStream_t stream);
 
 }  // namespace peclr

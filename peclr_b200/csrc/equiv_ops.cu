@@ -95,38 +95,46 @@ __global__ void rotation_matrix_kernel(const double* angle, const float* cx, con
 }
 
 // get_projection_stats (hybrid2_model.py:92-106): per sample mean / lower median / min / max over the m points of
-// coordinates 0 and 1, averaged over the batch.  out[8] = x{mean, median, min, max}, y{...}; zeroed by the host.
+// coordinates 0 and 1, averaged over the batch.  out[8] = x{mean, median, min, max}, y{...}.  ONE block: its warps
+// walk the samples and add their results in a fixed order (reproducible; the op is tiny and logging-only).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) projection_stats_kernel(const float* enc, float* out, int n,
                                                                                int m, int d) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const float* e = enc + (size_t)i * m * d;
-  const int target = (m - 1) / 2;  // torch.median returns the lower of the two middle values
-  float res[8];
+  __shared__ float part[kWarpsPerBlock][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mine = 0.f;  // lane j < 8 accumulates statistic j over this warp's samples
+  for (int i = warp; i < n; i += kWarpsPerBlock) {
+    const float* e = enc + (size_t)i * m * d;
+    const int target = (m - 1) / 2;  // torch.median returns the lower of the two middle values
+    float res[8];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    float sum = 0.f, lo = INFINITY, hi = -INFINITY, med = 0.f;
-    for (int k = lane; k < m; k += 32) {
-      const float v = e[(size_t)k * d + c];
-      sum += v, lo = fminf(lo, v), hi = fmaxf(hi, v);
-      int rank = 0;  // position of v in the sorted order, ties broken by index
-      for (int j = 0; j < m; ++j) {
-        const float o = e[(size_t)j * d + c];
-        rank += (o < v) || (o == v && j < k);
+    for (int c = 0; c < 2; ++c) {
+      float sum = 0.f, lo = INFINITY, hi = -INFINITY, med = 0.f;
+      for (int k = lane; k < m; k += 32) {
+        const float v = e[(size_t)k * d + c];
+        sum += v, lo = fminf(lo, v), hi = fmaxf(hi, v);
+        int rank = 0;  // position of v in the sorted order, ties broken by index
+        for (int j = 0; j < m; ++j) {
+          const float o = e[(size_t)j * d + c];
+          rank += (o < v) || (o == v && j < k);
+        }
+        if (rank == target) med = v;
       }
-      if (rank == target) med = v;
+      res[4 * c + 0] = warp_sum(sum) / (float)m;
+      res[4 * c + 1] = warp_sum(med);  // exactly one element has the target rank
+      res[4 * c + 2] = warp_min(lo);
+      res[4 * c + 3] = warp_max(hi);
     }
-    res[4 * c + 0] = warp_sum(sum) / (float)m;
-    res[4 * c + 1] = warp_sum(med);  // exactly one element has the target rank
-    res[4 * c + 2] = warp_min(lo);
-    res[4 * c + 3] = warp_max(hi);
-  }
-  if (lane < 8) {
     float v = res[0];
 #pragma unroll
     for (int j = 1; j < 8; ++j) v = lane == j ? res[j] : v;
-    atomicAdd(out + lane, v / (float)n);
+    mine += v;
+  }
+  if (lane < 8) part[warp][lane] = mine;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += part[w][threadIdx.x];
+    out[threadIdx.x] = t / (float)n;
   }
 }
 
@@ -175,10 +183,6 @@ extern "C" int peclr_rotation_2d_matrix(const double* angle, const float* center
 
 extern "C" int peclr_projection_stats(const float* enc, float* out8, int n, int m, int d, void* stream) {
   if (!enc || !out8 || n < 1 || m < 1 || d < 2) return -1001;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(out8, 0, 8 * sizeof(float), st);
-  if (e != cudaSuccess) return -(int)e;
-  projection_stats_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(enc, out8, n, m,
-                                                                                                    d);
+  projection_stats_kernel<<<1, kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(enc, out8, n, m, d);
   return check_launch();
 }

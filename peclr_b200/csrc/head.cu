@@ -9,12 +9,15 @@
 namespace peclr {
 
 // C[m, n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]);  32x32 tile, 256 threads, 2x2 each.
-// The GEMMs of the head are tiny (M = 2B rows): blockIdx.z splits K so that a launch fills the machine; with more
-// than one split the partial sums are added atomically into C (zeroed by the host unless it accumulates).
+// The GEMMs of the head are tiny (M = 2B rows): blockIdx.z splits K so that a launch fills the machine.  With more
+// than one split every block stores its partial tile to the workspace slab of its split; the LAST block to arrive
+// for a tile (counter in the workspace, self-resetting) adds the slabs in split order and writes C -- a fixed
+// summation order, so the result is reproducible (no floating-point atomics).
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                             float* C, const float* __restrict__ bias, int M, int N,
                                                             int K, long long sam, long long sak, long long sbk,
-                                                            long long sbn, long long ldc, int accumulate, int k_per) {
+                                                            long long sbn, long long ldc, int accumulate, int k_per,
+                                                            float* partial, unsigned* counters) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -53,16 +56,46 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     }
     __syncthreads();
   }
+  if (gridDim.z > 1) {
+    __shared__ int is_last;
+    const long long slab = (long long)M * N;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2 + j;
+        if (gm < M && gn < N) __stcg(partial + blockIdx.z * slab + (long long)gm * N + gn, acc[i][j]);
+      }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* ctr = counters + blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned prev = atomicAdd(ctr, 1u);
+      is_last = prev == gridDim.z - 1;
+      if (is_last) *ctr = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        acc[i][j] = 0.f;
+        const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2 + j;
+        if (gm < M && gn < N)
+          for (unsigned z = 0; z < gridDim.z; ++z) acc[i][j] += __ldcg(partial + z * slab + (long long)gm * N + gn);
+      }
+  }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2 + j;
       if (gm < M && gn < N) {
-        float v = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[gn] : 0.f);
+        const float v = acc[i][j] + (bias ? bias[gn] : 0.f);
         float* c = C + (long long)gm * ldc + gn;
-        if (gridDim.z > 1) atomicAdd(c, v);
-        else *c = accumulate ? *c + v : v;
+        *c = accumulate ? *c + v : v;
       }
     }
 }
@@ -190,24 +223,46 @@ static int head_last_error() {
   return e == cudaSuccess ? 0 : -(int)e;
 }
 
+// workspace layout: [tile counters, kCounterBytes][splits slabs of M*N floats].  The counters sit at a FIXED place
+// (K is only split while there are fewer than 2*148 tiles, so 512 counters always suffice): GEMMs of different
+// shapes can share one workspace without one's partials landing on another's (zero-at-rest) counters.
+constexpr long long kCounterBytes = 2048;
+// split K until there are about two blocks per SM (at least 64 of K per split, whole 32-wide k steps)
+static int sgemm_splits(int M, int N, int K, int* k_per) {
+  const int tiles = ((N + 31) / 32) * ((M + 31) / 32);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > K / 64) splits = K / 64;
+  if (splits < 1) splits = 1;
+  *k_per = ((K + splits - 1) / splits + 31) / 32 * 32;
+  return (K + *k_per - 1) / *k_per;
+}
+
+extern "C" long long peclr_sgemm_workspace_bytes(int M, int N, int K) {
+  if (M < 1 || N < 1 || K < 1) return -1001;
+  int k_per = 0;
+  const int splits = sgemm_splits(M, N, K, &k_per);
+  if (splits == 1) return 0;
+  return kCounterBytes + (long long)splits * M * N * 4;
+}
+
 extern "C" int peclr_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
                            long long sam, long long sak, long long sbk, long long sbn, long long ldc, int accumulate,
-                           void* stream) {
+                           void* workspace, long long workspace_bytes, void* stream) {
   if (M < 1 || N < 1 || K < 1) return -1001;
   dim3 grid((N + 31) / 32, (M + 31) / 32);
-  // split K until there are about two blocks per SM (at least 64 of K per split, whole 32-wide k steps)
-  int splits = (2 * 148 + (int)(grid.x * grid.y) - 1) / (int)(grid.x * grid.y);
-  if (splits > K / 64) splits = K / 64;
-  if (splits < 1 || ldc != N) splits = 1;
-  int k_per = ((K + splits - 1) / splits + 31) / 32 * 32;
-  splits = (K + k_per - 1) / k_per;
-  grid.z = splits;
-  if (splits > 1 && !accumulate) {
-    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) return -(int)e;
+  int k_per = 0;
+  int splits = sgemm_splits(M, N, K, &k_per);
+  // no (or too small a) workspace: one split per tile (still exact, just fewer blocks in flight)
+  if (splits > 1 && (!workspace || workspace_bytes < peclr_sgemm_workspace_bytes(M, N, K))) {
+    splits = 1;
+    k_per = (K + 31) / 32 * 32;
   }
+  grid.z = splits;
+  // the counters must be zero before the first use (the caller zeroes the workspace once; the kernel resets them)
+  unsigned* counters = static_cast<unsigned*>(workspace);
+  float* partial = splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(workspace) + kCounterBytes) : nullptr;
   sgemm_strided_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, M, N, K, sam, sak, sbk, sbn, ldc,
-                                                                accumulate, k_per);
+                                                                accumulate, k_per, partial, counters);
   return head_last_error();
 }
 

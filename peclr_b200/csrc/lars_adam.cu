@@ -22,7 +22,7 @@ struct OptArgs {
   const float* seg_wd;          // [T] weight decay of the tensor's param group
   const int* chunk_seg;         // [num_chunks] tensor id of each chunk
   const long long* chunk_begin; // [num_chunks]
-  float* norms;                 // [T][2] sum p^2, sum g^2
+  double* norms;                // [T][2] sum p^2, sum g^2: fp64 accumulators of per-block partials (order independent)
   float lr, step_size, bc2_sqrt, beta1, beta2, adam_eps, eta, lars_eps;
   int lars, clip;
 };
@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) opt_norms_kernel(const OptArgs a) {
   if (threadIdx.x == 0) {
     float x = 0.f, y = 0.f;
     for (int i = 0; i < 8; ++i) x += red[0][i], y += red[1][i];
-    atomicAdd(a.norms + 2 * t, x);
-    atomicAdd(a.norms + 2 * t + 1, y);
+    atomicAdd(a.norms + 2 * t, (double)x);
+    atomicAdd(a.norms + 2 * t + 1, (double)y);
   }
 }
 
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) opt_update_kernel(const OptArgs a) {
   const float wd = a.seg_wd[t];
   float trust = 1.f, wd_eff = 0.f;
   if (a.lars) {
-    const float pn = sqrtf(a.norms[2 * t]), gn = sqrtf(a.norms[2 * t + 1]);
+    const float pn = sqrtf((float)a.norms[2 * t]), gn = sqrtf((float)a.norms[2 * t + 1]);
     if (pn != 0.f && gn != 0.f) {
       trust = (a.eta * pn) / (gn + pn * wd + a.lars_eps);
       if (a.clip) trust = fminf(a.lr != 0.f ? trust / a.lr : INFINITY, 1.f);
@@ -158,7 +158,7 @@ static int opt_last_error() {
 
 extern "C" int peclr_lars_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16,
                                     const long long* seg_begin, const float* seg_wd, int num_segs,
-                                    const int* chunk_seg, const long long* chunk_begin, int num_chunks, float* norms,
+                                    const int* chunk_seg, const long long* chunk_begin, int num_chunks, double* norms,
                                     float lr, int step, float beta1, float beta2, float adam_eps, int lars, float eta,
                                     int clip, float lars_eps, void* stream) {
   if (num_chunks < 1 || num_segs < 1 || step < 1) return -1001;
@@ -173,7 +173,7 @@ extern "C" int peclr_lars_adam_step(float* p, const float* g, float* m, float* v
   a.beta1 = beta1, a.beta2 = beta2, a.adam_eps = adam_eps, a.eta = eta, a.lars_eps = lars_eps;
   a.lars = lars, a.clip = clip;
   if (lars) {
-    cudaError_t e = cudaMemsetAsync(norms, 0, sizeof(float) * 2 * num_segs, st);
+    cudaError_t e = cudaMemsetAsync(norms, 0, sizeof(double) * 2 * num_segs, st);
     if (e != cudaSuccess) return -(int)e;
     opt_norms_kernel<<<num_chunks, 256, 0, st>>>(a);
   }

@@ -19,6 +19,10 @@
 //   P4  one warp per local row: loss terms and the chain rule back to p.
 // Every rank recomputes neg for all global rows, so the backward needs no second collective
 // (SURVEY.md section 8(e)); gradients of the GLOBAL mean loss w.r.t. local rows come out complete.
+//
+// Reproducibility: nothing is accumulated with fp32 atomics.  Row sums, the loss and the statistics are added as
+// fp64 atomics (per-tile / per-block / per-row partials computed in a fixed order; their fp64 totals do not depend
+// on the arrival order), the gradient partials of the column chunks go to separate slabs that P4 adds in order.
 #include <math.h>
 
 #include "../../include/peclr_b200.h"
@@ -40,13 +44,14 @@ struct NtxentArgs {
   float* const* z_peers;   // [world] every rank's z buffer (device pointers), null when world == 1
   unsigned* const* flag_peers;  // [world] every rank's flag array [world], null when world == 1
   float* rowbuf;           // [2B][4]: 1/|p|, 1/|r|, alpha, beta
-  float* neg;              // [n_glob]
+  double* neg;             // [n_glob] fp64 accumulators of the row sums
+  double* acc;             // [17]: loss, 16 statistics (fp64 accumulators)
   float* spos;             // [n_glob]
-  float* gz;               // [2B][128]
+  float* gz;               // [chunks][2B][128]: one slab per P3 column chunk, added in order by P4
   float* loss;             // [1]
   float* stats;            // [16] proj1 x{mean,median,min,max}, y{...}, proj2 ...
   float* g_p;              // [2B][128], null for forward only
-  unsigned* barrier;       // [1] zeroed by the host before every launch
+  unsigned* barrier;       // [2] zeroed by the host before every launch: grid barrier, blocks done with the loss
   int B, world, rank;
   int img_h, img_w, crop, rotate;
   float inv_t;
@@ -103,16 +108,12 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   float* const zbuf = a.z + zsel;
 
   // ---------------------------------------------------------------- P1
-  if (blockIdx.x == 0 && threadIdx.x < 17) {
-    if (threadIdx.x == 16) *a.loss = 0.f;
-    else if (a.stats) a.stats[threadIdx.x] = 0.f;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_glob; i += gridDim.x * blockDim.x) a.neg[i] = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x < 17) a.acc[threadIdx.x] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_glob; i += gridDim.x * blockDim.x) a.neg[i] = 0.0;
   for (int i = gwarp; i < n_loc; i += nwarps) {
     const float4 v = reinterpret_cast<const float4*>(a.p + (size_t)i * D)[lane];  // points 2l, 2l+1
     if (a.plain) {
       reinterpret_cast<float4*>(zbuf + (size_t)global_row(i, a.B, a.world, a.rank) * D)[lane] = v;
-      if (a.g_p) reinterpret_cast<float4*>(a.gz + (size_t)i * D)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
     float x0 = v.x, y0 = v.y, x1 = v.z, y1 = v.w;
@@ -122,11 +123,10 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
       const float lox = warp_min(fminf(x0, x1)), hix = warp_max(fmaxf(x0, x1));
       const float loy = warp_min(fminf(y0, y1)), hiy = warp_max(fmaxf(y0, y1));
       const float medx = warp_lower_median64(x0, x1, lane), medy = warp_lower_median64(y0, y1, lane);
-      if (lane == 0) {
-        float* s = a.stats + (i < a.B ? 0 : 8);
-        const float w = 1.f / (float)a.B;
-        atomicAdd(s + 0, mx * w), atomicAdd(s + 1, medx * w), atomicAdd(s + 2, lox * w), atomicAdd(s + 3, hix * w);
-        atomicAdd(s + 4, my * w), atomicAdd(s + 5, medy * w), atomicAdd(s + 6, loy * w), atomicAdd(s + 7, hiy * w);
+      if (lane < 8) {  // fp64 sums over the batch (block 0 converts them in P4)
+        const float v8 = lane == 0 ? mx : lane == 1 ? medx : lane == 2 ? lox : lane == 3 ? hix
+                       : lane == 4 ? my : lane == 5 ? medy : lane == 6 ? loy : hiy;
+        atomicAdd(a.acc + 1 + (i < a.B ? 0 : 8) + lane, (double)v8);
       }
     }
     const float pn = sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1));
@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         reinterpret_cast<float4*>(a.z_peers[r] + zsel + (size_t)gi * D)[lane] = zv;
     }
     if (lane == 0) reinterpret_cast<float4*>(a.rowbuf)[i] = make_float4(inv_p, inv_r, al, be);
-    if (a.g_p) reinterpret_cast<float4*>(a.gz + (size_t)i * D)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   bar_target += gridDim.x;
   grid_barrier(a.barrier, bar_target);
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         // the 16 threads sharing a row are consecutive lanes of a half warp
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
-        if (tc == 0 && gi < n_glob) atomicAdd(a.neg + gi, rowsum);
+        if (tc == 0 && gi < n_glob) atomicAdd(a.neg + gi, (double)rowsum);
       }
     }
   }
@@ -290,13 +289,13 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         for (int r = 0; r < 2; ++r) {
           const int li = i0 + 2 * tr + r;
           const int gi = li < n_loc ? global_row(li, a.B, a.world, a.rank) : -1;
-          const float inv_ni = gi >= 0 ? 1.f / a.neg[gi] : 0.f;
+          const float inv_ni = gi >= 0 ? 1.f / (float)a.neg[gi] : 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int gk = k0 + tc + 16 * c;
             float coef = 0.f;
             if (gi >= 0 && gk < kend && gk != gi) {
-              coef = __expf(acc[r][c] * a.inv_t) * (inv_ni + 1.f / a.neg[gk]);
+              coef = __expf(acc[r][c] * a.inv_t) * (inv_ni + 1.f / (float)a.neg[gk]);
               if (gk == (gi + half) % n_glob) coef -= 2.f;
               coef *= scale;
             }
@@ -318,15 +317,10 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
         }
       }
       const int li = i0 + orow;
-      if (li < n_loc) {
-        float* dst = a.gz + (size_t)li * D + of;
+      if (li < n_loc) {  // this chunk's slab (plain stores; an empty chunk stores zeros)
+        float* dst = a.gz + ((size_t)(u % chunks) * n_loc + li) * D + of;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          atomicAdd(dst + 32 * j + 0, out[j].x);
-          atomicAdd(dst + 32 * j + 1, out[j].y);
-          atomicAdd(dst + 32 * j + 2, out[j].z);
-          atomicAdd(dst + 32 * j + 3, out[j].w);
-        }
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 32 * j) = out[j];
       }
     }
     bar_target += gridDim.x;
@@ -336,23 +330,42 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
   // ---------------------------------------------------------------- P4: loss + chain rule to p
   // loss = (1/n) sum_i (log neg_i - S_i,pos(i)/T) over ALL global rows (every rank gets the global loss)
   {
+    __shared__ float wpart[8];
     float part = 0.f;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_glob; g += gridDim.x * blockDim.x)
-      part += logf(a.neg[g]) - a.spos[g];
+      part += logf((float)a.neg[g]) - a.spos[g];
     part = warp_sum(part);
-    if (lane == 0 && part != 0.f) atomicAdd(a.loss, part / (float)n_glob);
+    if (lane == 0) wpart[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float bp = 0.f;
+      for (int w = 0; w < 8; ++w) bp += wpart[w];
+      atomicAdd(a.acc, (double)bp);
+      __threadfence();
+      if (atomicAdd(a.barrier + 1, 1u) == gridDim.x - 1) {  // last block: every partial is in
+        __threadfence();
+        *a.loss = (float)(*reinterpret_cast<volatile double*>(a.acc) / (double)n_glob);
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 16 && a.stats)  // (P1's sums were complete at the first grid barrier)
+      a.stats[threadIdx.x] = (float)(a.acc[1 + threadIdx.x] / (double)a.B);
   }
   if (!a.g_p) return;
+  const int gz_chunks = (n_glob + a.col_chunk - 1) / a.col_chunk;
   for (int i = gwarp; i < n_loc; i += nwarps) {
     const int gi = global_row(i, a.B, a.world, a.rank);
+    float4 g = reinterpret_cast<const float4*>(a.gz + (size_t)i * D)[lane];
+    for (int c = 1; c < gz_chunks; ++c) {  // slab order = fixed summation order
+      const float4 v = reinterpret_cast<const float4*>(a.gz + ((size_t)c * n_loc + i) * D)[lane];
+      g.x += v.x, g.y += v.y, g.z += v.z, g.w += v.w;
+    }
     if (a.plain) {
-      reinterpret_cast<float4*>(a.g_p + (size_t)i * D)[lane] = reinterpret_cast<const float4*>(a.gz + (size_t)i * D)[lane];
+      reinterpret_cast<float4*>(a.g_p + (size_t)i * D)[lane] = g;
       continue;
     }
     const float4 rb = reinterpret_cast<const float4*>(a.rowbuf)[i];
     const float inv_p = rb.x, inv_r = rb.y, al = rb.z, be = rb.w;
     const float4 zv = reinterpret_cast<const float4*>(zbuf + (size_t)gi * D)[lane];
-    const float4 g = reinterpret_cast<const float4*>(a.gz + (size_t)i * D)[lane];
     // through the second normalisation: g_r = (g_z - z (z . g_z)) / |r|
     const float dot = warp_sum(zv.x * g.x + zv.y * g.y + zv.z * g.z + zv.w * g.w);
     float gx0 = (g.x - zv.x * dot) * inv_r, gy0 = (g.y - zv.y * dot) * inv_r;
@@ -379,11 +392,49 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
 
 using namespace peclr;
 
+// launch geometry shared by the workspace query and the launch: grid, P3 column chunks
+static void ntxent_plan(long long n_loc, long long n_glob, int* grid_out, int* chunks_out, int* col_chunk_out) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  const int p2_units = (int)(((n_glob + RB - 1) / RB) * ((n_glob + CB - 1) / CB));
+  int grid = p2_units < sms ? p2_units : sms;
+  if (grid < 1) grid = 1;
+  // P3: split the columns so that there are about 2 units per CTA
+  const int rbs = (int)((n_loc + RB - 1) / RB);
+  int chunks = (2 * grid + rbs - 1) / rbs;
+  const int max_chunks = (int)((n_glob + CB - 1) / CB);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int col_chunk = (int)(((n_glob + chunks - 1) / chunks + CB - 1) / CB) * CB;
+  *grid_out = grid;
+  *chunks_out = (int)((n_glob + col_chunk - 1) / col_chunk);
+  *col_chunk_out = col_chunk;
+}
+
+// workspace layout (in floats): z [1 or 2][n_glob][128] | neg double[n_glob] | acc double[18] | rowbuf [n_loc][4] |
+// spos [n_glob, padded to 4] | gz [chunks][n_loc][128] | barrier, done, ..., launch counter
+static long long ntxent_layout(long long n_loc, long long n_glob, int world, int chunks, long long* off) {
+  const long long zbufs = world > 1 ? 2 : 1;
+  off[0] = zbufs * n_glob * D;                    // neg
+  off[1] = off[0] + 2 * n_glob;                   // acc
+  off[2] = off[1] + 36;                           // rowbuf
+  off[3] = off[2] + n_loc * 4;                    // spos
+  off[4] = off[3] + (n_glob + 3) / 4 * 4;         // gz
+  off[5] = off[4] + (long long)chunks * n_loc * D;  // barrier block (16 words)
+  return 4 * (off[5] + 64);
+}
+
 extern "C" long long peclr_ntxent_workspace_bytes(int B, int world) {
   const long long n_loc = 2LL * B, n_glob = n_loc * world;
-  // z [1 or 2][n_glob][128] | rowbuf [n_loc][4] | neg [n_glob] | spos [n_glob] | gz [n_loc][128] | barrier, counter
-  const long long zbufs = world > 1 ? 2 : 1;
-  return 4 * (zbufs * n_glob * D + n_loc * 4 + 2 * n_glob + n_loc * D) + 256;
+  int grid, chunks, col_chunk;
+  ntxent_plan(n_loc, n_glob, &grid, &chunks, &col_chunk);
+  long long off[6];
+  return ntxent_layout(n_loc, n_glob, world, chunks, off);
 }
 
 static int ntxent_launch(const float* p, const double* angle, const long long* jx, const long long* jy, int B,
@@ -395,15 +446,20 @@ static int ntxent_launch(const float* p, const double* angle, const long long* j
   if ((crop && (!jx || !jy)) || (rotate && !angle)) return -1001;
   if (world > 1 && (!z_peers || !flag_peers || world > 32)) return -1001;
   const long long n_loc = 2LL * B, n_glob = n_loc * world;
+  int grid, chunks, col_chunk;
+  ntxent_plan(n_loc, n_glob, &grid, &chunks, &col_chunk);
+  long long off[6];
+  ntxent_layout(n_loc, n_glob, world, chunks, off);
   NtxentArgs a;
   float* ws = static_cast<float*>(workspace);
   a.p = p, a.angle = angle, a.jx = jx, a.jy = jy;
   a.z = ws;
-  a.rowbuf = a.z + (world > 1 ? 2 : 1) * n_glob * D;
-  a.neg = a.rowbuf + n_loc * 4;
-  a.spos = a.neg + n_glob;
-  a.gz = a.spos + n_glob;
-  a.barrier = reinterpret_cast<unsigned*>(a.gz + n_loc * D);
+  a.neg = reinterpret_cast<double*>(ws + off[0]);
+  a.acc = reinterpret_cast<double*>(ws + off[1]);
+  a.rowbuf = ws + off[2];
+  a.spos = ws + off[3];
+  a.gz = ws + off[4];
+  a.barrier = reinterpret_cast<unsigned*>(ws + off[5]);
   a.launch_ctr = a.barrier + 8;  // lives in the (zero-initialised) workspace, advanced by the kernel
   a.z_peers = z_peers, a.flag_peers = flag_peers;
   a.loss = loss, a.stats = stats, a.g_p = g_p;
@@ -412,20 +468,8 @@ static int ntxent_launch(const float* p, const double* angle, const long long* j
   a.inv_t = 1.f / temperature;
   a.plain = plain;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int p2_units = (int)(((n_glob + RB - 1) / RB) * ((n_glob + CB - 1) / CB));
-  int grid = p2_units < sms ? p2_units : sms;
-  if (grid < 1) grid = 1;
-  // P3: split the columns so that there are about 2 units per CTA
-  const int rbs = (int)((n_loc + RB - 1) / RB);
-  int chunks = (2 * grid + rbs - 1) / rbs;
-  const int max_chunks = (int)((n_glob + CB - 1) / CB);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  a.col_chunk = (int)(((n_glob + chunks - 1) / chunks + CB - 1) / CB) * CB;
-  cudaError_t e = cudaMemsetAsync(a.barrier, 0, 4, st);
+  a.col_chunk = col_chunk;
+  cudaError_t e = cudaMemsetAsync(a.barrier, 0, 8, st);
   if (e != cudaSuccess) return -(int)e;
   const size_t smem = sizeof(float) * (RB * LDS + CB * LDS + RB * (CB + 1));
   e = cudaFuncSetAttribute(ntxent_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -45,6 +45,10 @@ class StepEngine:
         self.overlap_wgrad = os.environ.get("PECLR_OVERLAP_WGRAD", "1") != "0"
         self.fuse_bn_reduce = os.environ.get("PECLR_FUSE_BN_REDUCE", "1") != "0"
         self._side = None
+        # workspaces of the split reductions (ordered, atomics-free: see include/peclr_b200.h).  The conv weight
+        # gradients share one (they run in order on one stream), the stem's runs on the main stream and has its own;
+        # the head's holds zero-at-rest tile counters.
+        self._wgrad_ws, self._stem_ws, self._head_ws = ops.Workspace(), ops.Workspace(), ops.Workspace(zero=True)
 
     # ------------------------------------------------------------------ parameter arena
     def _trainable(self):
@@ -193,7 +197,7 @@ class StepEngine:
         if self.weights_dirty:
             self.sync_weights()
         b, _, h, w = img1.shape
-        n = 2 * b
+        n = 2 * b if img2 is not None else b  # img2 None: img1 is the whole batch (any size)
         dev = self.device
         ctx = {"n": n, "hw": (h, w), "blocks": []}
         convs = [self.stem_conv] + [c for blk in self.blocks for c, _ in blk.convs()] + \
@@ -268,7 +272,7 @@ class StepEngine:
     def forward_head(self, enc, training=True):
         lin1, bn, _, lin2 = self.head
         h1 = ops.linear_fwd(enc, self._p(lin1, "weight").view(lin1.out_features, lin1.in_features),
-                            self._p(lin1, "bias"))
+                            self._p(lin1, "bias"), ws=self._head_ws)
         if training:
             a1, saved = ops.bn1d_relu_fwd(h1, self._p(bn, "weight"), self._p(bn, "bias"),
                                           (bn.running_mean, bn.running_var), bn.eps, bn.momentum)
@@ -277,14 +281,13 @@ class StepEngine:
             scale = self._p(bn, "weight") * torch.rsqrt(bn.running_var + bn.eps)
             a1 = torch.relu(h1 * scale + (self._p(bn, "bias") - bn.running_mean * scale))
             saved = None
-        p = ops.linear_fwd(a1, self._p(lin2, "weight").view(lin2.out_features, lin2.in_features))
+        p = ops.linear_fwd(a1, self._p(lin2, "weight").view(lin2.out_features, lin2.in_features), ws=self._head_ws)
         return p, (enc, h1, a1, saved)
 
     def encode(self, x):
-        """Inference-style trunk forward on concatenated fp32 NCHW images (uses the module's train/eval mode)."""
-        half = x.shape[0] // 2
-        assert x.shape[0] % 2 == 0, "the trunk processes the two views as one even-sized batch"
-        enc, _ = self.forward_trunk(x[:half].contiguous(), x[half:].contiguous(), training=self.model.training)
+        """Inference-style trunk forward on fp32 NCHW images, any batch size -- as the reference's ``encoder(x)``
+        (uses the module's train/eval mode)."""
+        enc, _ = self.forward_trunk(x.contiguous(), None, training=self.model.training)
         return enc
 
     # ------------------------------------------------------------------ loss
@@ -332,12 +335,13 @@ class StepEngine:
         lin1, bn, _, lin2 = self.head
         w2 = self._p(lin2, "weight").view(lin2.out_features, lin2.in_features)
         w1 = self._p(lin1, "weight").view(lin1.out_features, lin1.in_features)
-        ops.linear_wgrad(g_p, a1, self._g(lin2, "weight").view_as(w2))
-        da1 = ops.linear_dgrad(g_p, w2)
+        hw = self._head_ws
+        ops.linear_wgrad(g_p, a1, self._g(lin2, "weight").view_as(w2), ws=hw)
+        da1 = ops.linear_dgrad(g_p, w2, ws=hw)
         dh1 = ops.bn1d_relu_bwd(da1, a1, h1, saved, self._p(bn, "weight"), self._g(bn, "weight"), self._g(bn, "bias"))
-        ops.linear_wgrad(dh1, enc, self._g(lin1, "weight").view_as(w1))
+        ops.linear_wgrad(dh1, enc, self._g(lin1, "weight").view_as(w1), ws=hw)
         ops.colsum_acc(dh1, self._g(lin1, "bias"))
-        return ops.linear_dgrad(dh1, w1)
+        return ops.linear_dgrad(dh1, w1, ws=hw)
 
     def backward_trunk(self, d_enc, ctx, after_stage=None):
         """after_stage(i): called when the gradients of ResNet stage i (and everything after it) are final --
@@ -354,6 +358,9 @@ class StepEngine:
             self._side = torch.cuda.Stream(device=dev)
         side, keep = self._side, []
         overlap = self.overlap_wgrad
+        # size the weight-gradient workspace for the largest launch of this pass up front (on the main stream, so the
+        # side stream never sees it reallocated under a running kernel)
+        self._wgrad_ws.get(self._max_wgrad_bytes(ctx), dev)
 
         def wgrad(fn, *alive):
             if not overlap:
@@ -379,8 +386,8 @@ class StepEngine:
             dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
                                     self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
             da = None
-            wgrad(lambda x=x, dy=dy, conv=conv: ops.conv2d_wgrad(x, dy, conv.k, conv.stride,
-                                                                  dw=self._g(conv, "weight")), x, dy)
+            wgrad(lambda x=x, dy=dy, conv=conv: ops.conv2d_wgrad(
+                x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"), ws=self._wgrad_ws), x, dy)
             cur_hw = (x.shape[1], x.shape[2])
             for i in range(len(convs) - 1, 0, -1):
                 conv, bn, x, y, act, sv = convs[i]
@@ -396,15 +403,15 @@ class StepEngine:
                 dy = ops.bn_backward(dx, None, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
                                      self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"),
                                      reduce_done=fused)
-                wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(px, dy, pconv.k, pconv.stride,
-                                                                         dw=self._g(pconv, "weight")), px, dy)
+                wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(
+                    px, dy, pconv.k, pconv.stride, dw=self._g(pconv, "weight"), ws=self._wgrad_ws), px, dy)
             conv1 = convs[0][0]
             if "down" in rec:
                 dconv, dbn, yd, dsv = rec["down"]
                 dyd = ops.bn_backward(g, None, yd, dsv, self._p(dbn, "weight"), self._g(dbn, "weight"),
                                       self._g(dbn, "bias"), scratch=scratch, dy=g)
-                wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: ops.conv2d_wgrad(a_in, dyd, 1, dconv.stride,
-                                                                               dw=self._g(dconv, "weight")), a_in, dyd)
+                wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: ops.conv2d_wgrad(
+                    a_in, dyd, 1, dconv.stride, dw=self._g(dconv, "weight"), ws=self._wgrad_ws), a_in, dyd)
                 da = ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride)
                 ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride, out=da, accumulate=True)
             else:
@@ -419,13 +426,27 @@ class StepEngine:
         bn0 = self.stem_bn
         dy0 = ops.stem_pool_bn_backward(da, pool_idx, y0, sv0, self._p(bn0, "weight"), self._p(bn0, "bias"),
                                         self._g(bn0, "weight"), self._g(bn0, "bias"), scratch=scratch)
-        dwp = ops.stem_wgrad(xpad, dy0, h, w)
+        dwp = ops.stem_wgrad(xpad, dy0, h, w, ws=self._stem_ws)
         _lib.call("peclr_stem_unpack_grad", dwp, self._g(self.stem_conv, "weight"), ops._s())
         if overlap:
             main.wait_stream(side)  # join: all weight gradients are complete when backward returns
         keep.clear()
         if after_stage is not None:
             after_stage(-1)
+
+    def _max_wgrad_bytes(self, ctx):
+        key = (ctx["n"], ctx["hw"])
+        cache = self.__dict__.setdefault("_wgrad_bytes_cache", {})
+        if key not in cache:
+            need = 0
+            for rec in ctx["blocks"]:
+                shapes = [(tuple(x.shape), conv.cout, conv.k, conv.stride) for conv, _, x, _, _, _ in rec["convs"]]
+                if "down" in rec:
+                    shapes.append((tuple(rec["a_in"].shape), rec["down"][0].cout, 1, rec["down"][0].stride))
+                for (n, h, w, cin), cout, k, stride in shapes:
+                    need = max(need, _lib.call("peclr_conv2d_wgrad_workspace_bytes", n, h, w, cin, cout, k, stride))
+            cache[key] = need
+        return cache[key]
 
     # ------------------------------------------------------------------ optimiser plumbing
     def optimizer_tables(self, weight_decay):

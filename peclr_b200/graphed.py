@@ -17,15 +17,26 @@ class GraphedStep:
         self.grad_scale = grad_scale
         self.graph = torch.cuda.CUDAGraph()
         model.train()
+        # The warm-up below runs real steps; gradients are zeroed by the caller afterwards, but BatchNorm running
+        # statistics / num_batches_tracked would keep the extra momentum updates (also right after a resume, when they
+        # were just restored from a checkpoint): snapshot them here and put them back after the warm-up.
+        eng = model.engine
+        bn_state = [(b, b.clone()) for m in model.modules() for n, b in m._buffers.items()
+                    if b is not None and n in ("running_mean", "running_var")]
+        nbt_state = eng.nbt.clone() if eng.nbt is not None else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # allocator / lazy-init warm-up outside the capture
                 out = model.forward_backward(self.static, grad_scale)
         torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            for b, saved in bn_state:
+                b.copy_(saved)
+            if nbt_state is not None:
+                eng.nbt.copy_(nbt_state)
         torch.cuda.synchronize()
-        # the warm-up steps must not leak into the user's gradient / BN state more than a real step would:
-        # callers zero the gradients before the first replay (Trainer and bench do).
+        # (gradients: callers zero them before the first replay -- Trainer and bench do; nothing runs during capture)
         from . import _lib
 
         before = _lib.LAUNCHES

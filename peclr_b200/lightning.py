@@ -74,6 +74,7 @@ class ModelCheckpoint(Callback):
     def __init__(self, save_top_k=1, period=1, monitor="checkpoint_saving_loss", dirpath=None):
         self.save_top_k, self.period, self.monitor, self.dirpath = save_top_k, period, monitor, dirpath
         self.best: List[tuple] = []  # (value, path)
+        self._pending = None
 
     def _save_model(self, filepath: str, trainer, pl_module):
         print(f"Saving checkpoint at {filepath}")  # (UpdatedModelCheckpoint, callbacks/model_checkpoint.py:5-10)
@@ -84,8 +85,32 @@ class ModelCheckpoint(Callback):
             "state_dict": pl_module.state_dict(),
             "optimizer_states": [o.state_dict() for o in trainer.optimizers],
             "lr_schedulers": [s["scheduler"].state_dict() for s in trainer.lr_schedulers],
+            # top-k bookkeeping (so that a resumed run keeps pruning the files of the run it continues) and where the
+            # encoder's initial weights came from (ImageNet file or random: see ResNetModel._init_like_reference)
+            "callbacks": {"ModelCheckpoint": {"best": [(v, p) for v, p in self.best] + [(self._pending, filepath)],
+                                              "monitor": self.monitor}},
+            "init_source": getattr(getattr(pl_module, "encoder", None), "init_source", None),
         }
         torch.save(ckpt, filepath)
+
+    def restore_state(self, ckpt: dict, ckpt_path: str):
+        """Rebuilds the top-k list on resume: from the checkpoint's own record, else (a checkpoint written by the
+        reference) from the ``epoch=N.ckpt`` files next to it, with an unknown (infinite) metric: they are the
+        first to be pruned once better-ranked checkpoints exist."""
+        rec = (ckpt.get("callbacks") or {}).get("ModelCheckpoint")
+        if rec and rec.get("best"):
+            best = [(float(v), p) for v, p in rec["best"] if os.path.exists(p)]
+        else:
+            d = os.path.dirname(os.path.abspath(ckpt_path))
+            found = []
+            for name in os.listdir(d):
+                if name.startswith("epoch=") and name.endswith(".ckpt"):
+                    try:
+                        found.append((int(name[len("epoch="):-len(".ckpt")]), os.path.join(d, name)))
+                    except ValueError:
+                        pass
+            best = [(float("inf"), p) for _, p in sorted(found)]
+        self.best = sorted(best, key=lambda t: t[0])
 
     def on_epoch_end(self, trainer, module):
         if trainer.global_rank != 0 or self.save_top_k == 0 or (trainer.current_epoch + 1) % self.period:
@@ -97,6 +122,7 @@ class ModelCheckpoint(Callback):
         dirpath = self.dirpath or os.path.join(trainer.default_root_dir, "checkpoints")
         path = os.path.join(dirpath, f"epoch={trainer.current_epoch}.ckpt")
         if self.save_top_k < 0 or len(self.best) < self.save_top_k or value < max(v for v, _ in self.best):
+            self._pending = value
             self._save_model(path, trainer, module)
             self.best.append((value, path))
             self.best.sort(key=lambda t: t[0])
@@ -162,6 +188,25 @@ class Trainer:
         self.optimizers, self.lr_schedulers = [], []
         self.images_per_sec = None
 
+    @staticmethod
+    def _with_last_flag(loader, limit):
+        """(index, batch, is_last_batch_of_the_epoch) with one batch of look-ahead."""
+        it = iter(loader)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        idx = 0
+        while True:
+            try:
+                nxt = next(it) if (limit is None or idx + 1 < limit) else None
+            except StopIteration:
+                nxt = None
+            yield idx, cur, nxt is None
+            if nxt is None:
+                return
+            cur, idx = nxt, idx + 1
+
     def _to_device(self, batch, device):
         return {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
 
@@ -176,6 +221,9 @@ class Trainer:
         for sch, sd in zip(self.lr_schedulers, ckpt.get("lr_schedulers", [])):
             sch["scheduler"].load_state_dict(sd)
         self.global_step = int(ckpt.get("global_step", 0))
+        for cb in self.callbacks:
+            if isinstance(cb, ModelCheckpoint):
+                cb.restore_state(ckpt, path)
         return int(ckpt.get("epoch", -1)) + 1
 
     def fit(self, model: LightningModule, train_dataloader, val_dataloader=None):
@@ -185,6 +233,11 @@ class Trainer:
         if self.world_size > 1:
             model.engine.world, model.engine.rank = self.world_size, self.global_rank
         model.setup("fit")
+        init_source = getattr(getattr(model, "encoder", None), "init_source", None)
+        if init_source is not None and self.global_rank == 0:
+            print(f"encoder initial weights: {init_source}")
+            if self.logger:
+                self.logger.log_hyperparams({"encoder_init_source": init_source})
         opts, scheds = model.configure_optimizers()
         self.optimizers, self.lr_schedulers = opts, scheds
         opt, sched = opts[0], scheds[0]["scheduler"]
@@ -197,9 +250,7 @@ class Trainer:
             model.train()
             outputs = []
             t0, seen = time.time(), 0
-            for batch_idx, batch in enumerate(train_dataloader):
-                if self.limit_train_batches is not None and batch_idx >= self.limit_train_batches:
-                    break
+            for batch_idx, batch, is_last in self._with_last_flag(train_dataloader, self.limit_train_batches):
                 batch = self._to_device(batch, device)
                 if self.use_cuda_graph:
                     # same work as the eager branch below, submitted as one captured CUDA graph
@@ -220,7 +271,10 @@ class Trainer:
                     (out["loss"] / acc).backward()
                     outputs.append({k: v.detach() for k, v in out.items()})
                 seen += 2 * batch["transformed_image1"].shape[0] * self.world_size
-                if (batch_idx + 1) % acc == 0:
+                # Lightning 1.0.8 steps when the accumulation window is full AND on the final batch of the epoch (a
+                # partial window: the loss keeps its 1 / accumulate_grad_batches scale), so no gradient leaks into
+                # the next epoch's first window
+                if (batch_idx + 1) % acc == 0 or is_last:
                     model.sync_gradients()
                     opt.step()
                     opt.zero_grad()

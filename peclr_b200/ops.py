@@ -15,19 +15,41 @@ def _s():
 f64 = torch.float64  # the conv epilogue's BatchNorm sums are fp64 accumulators (order independent -> reproducible)
 
 
-def stat_replicas():
-    """R: a BN-backward scratch buffer holds R fp32 accumulator sets (include/peclr_b200.h)."""
-    return _lib.call("peclr_stat_replicas")
-
-
 def new_stats(c, device):
     """Zeroed [2][C] fp64 buffer for the conv epilogue's per-channel sum / sum of squares."""
     return torch.zeros((2, c), dtype=f64, device=device)
 
 
 def new_scratch(c, device):
-    """[R][2C] fp32 buffer for the BN-backward sums (zeroed by the kernels that fill it)."""
-    return torch.empty((stat_replicas() * 2 * c,), dtype=torch.float32, device=device)
+    """[2C] fp64 accumulators for the BN-backward sums (zeroed by the kernels that fill them)."""
+    return torch.empty((2 * c,), dtype=f64, device=device)
+
+
+class Workspace:
+    """A grow-only device buffer for the split reductions (weight-gradient pixel splits, head split-K).  One per
+    stream that issues such kernels: consecutive launches on a stream reuse it in order."""
+
+    def __init__(self, zero=False):
+        self.buf, self.zero = None, zero
+
+    def get(self, nbytes, device):
+        if nbytes <= 0:
+            return None, 0
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            make = torch.zeros if self.zero else torch.empty
+            self.buf = make((int(nbytes),), dtype=torch.uint8, device=device)
+        return self.buf, self.buf.numel()
+
+
+_DEFAULT_WS = {}
+
+
+def _default_ws(kind, zero=False):
+    """Per-(kind, stream) workspace for callers that do not manage one (tests, stand-alone op calls)."""
+    key = (kind, torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    if key not in _DEFAULT_WS:
+        _DEFAULT_WS[key] = Workspace(zero=zero)
+    return _DEFAULT_WS[key]
 
 
 def _sums(t):
@@ -71,7 +93,7 @@ def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False):
 def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta, scratch, out=None):
     """dgrad whose epilogue also accumulates the BatchNorm-backward sums of the BN + ReLU in front of the conv
     (scratch [R][2*Cin] fp32 sets: sum g, sum g*y).  Follow with bn_backward(..., scratch=scratch, reduce_done=True)."""
-    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 2 * in_shape[-1]
+    assert scratch.dtype == f64 and scratch.numel() >= 2 * in_shape[-1]
     _need_cuda(dy, wt, bn_y)
     n, h, wd, cin = in_shape
     cout = dy.shape[-1]
@@ -81,14 +103,18 @@ def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta,
     return dx
 
 
-def conv2d_wgrad(x, dy, k, stride, dw=None):
-    """dw [Cout,k*k,Cin] fp32 += dy^T im2col(x)."""
+def conv2d_wgrad(x, dy, k, stride, dw=None, ws=None):
+    """dw [Cout,k*k,Cin] fp32 += dy^T im2col(x).  ws: the Workspace the pixel splits' partials go through."""
     _need_cuda(x, dy)
     n, h, wd, cin = x.shape
     cout = dy.shape[-1]
     if dw is None:
         dw = torch.zeros((cout, k * k, cin), dtype=torch.float32, device=x.device)
-    _lib.call("peclr_conv2d_wgrad", x, dy, dw, n, h, wd, cin, cout, k, stride, _s())
+    need = _lib.call("peclr_conv2d_wgrad_workspace_bytes", n, h, wd, cin, cout, k, stride)
+    if need < 0:
+        raise _lib.PeclrKernelError("peclr_conv2d_wgrad: unsupported geometry")
+    buf, nbytes = (ws or _default_ws("wgrad")).get(need, x.device)
+    _lib.call("peclr_conv2d_wgrad", x, dy, dw, n, h, wd, cin, cout, k, stride, buf, nbytes, _s())
     return dw
 
 
@@ -97,9 +123,10 @@ def stem_input(img1, img2, out=None):
     16-channel pixels, block (Y, X) at (Y+2, X+2), channel = dy*6 + dx*3 + c)."""
     _need_cuda(img1, img2)
     b, c, h, w = img1.shape
-    assert c == 3 and img2.shape == img1.shape and img1.dtype == torch.float32
-    if out is None:
-        out = torch.empty((2 * b, h // 2 + 3, w // 2 + 4, 16), dtype=bf16, device=img1.device)
+    assert c == 3 and img1.dtype == torch.float32 and (img2 is None or img2.shape == img1.shape)
+    if out is None:  # img2 None: img1 alone (any batch size)
+        out = torch.empty(((2 if img2 is not None else 1) * b, h // 2 + 3, w // 2 + 4, 16), dtype=bf16,
+                          device=img1.device)
     _lib.call("peclr_stem_input", img1, img2, out, b, h, w, _s())
     return out
 
@@ -125,11 +152,13 @@ def stem_fprop(xpad, wpack, h, w, want_stats=False, out=None, stats=None):
     return (y, stats) if want_stats else y
 
 
-def stem_wgrad(xpad, dy, h, w, dwpack=None):
+def stem_wgrad(xpad, dy, h, w, dwpack=None, ws=None):
     n = xpad.shape[0]
     if dwpack is None:
         dwpack = torch.zeros((64, 4, 64), dtype=torch.float32, device=xpad.device)
-    _lib.call("peclr_stem_wgrad", xpad, dy, dwpack, n, h, w, _s())
+    need = _lib.call("peclr_stem_wgrad_workspace_bytes", n, h, w)
+    buf, nbytes = (ws or _default_ws("wgrad")).get(need, xpad.device)
+    _lib.call("peclr_stem_wgrad", xpad, dy, dwpack, n, h, w, buf, nbytes, _s())
     return dwpack
 
 
@@ -169,7 +198,7 @@ def bn_backward(dout, mask, y, saved, gamma, dgamma, dbeta, want_g=False, scratc
     mode = (3 if mask.dtype == torch.uint8 else 1) if mask is not None else (2 if beta is not None else 0)
     if scratch is None:
         scratch = new_scratch(c, y.device)
-    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 2 * c
+    assert scratch.dtype == f64 and scratch.numel() >= 2 * c
     dy = dy if dy is not None else torch.empty_like(y)
     if want_g and g_out is None:
         g_out = torch.empty_like(y)
@@ -201,7 +230,7 @@ def stem_pool_bn_backward(dpool, idx, y, saved, gamma, beta, dgamma, dbeta, g_bu
     n, h, w, c = y.shape
     if scratch is None:
         scratch = new_scratch(64, y.device)
-    assert scratch.dtype == torch.float32 and scratch.numel() >= stat_replicas() * 128
+    assert scratch.dtype == f64 and scratch.numel() >= 128
     g = g_buf if g_buf is not None else torch.empty_like(y)
     _lib.call("peclr_stem_pool_bwd", dpool, idx, y, saved[0], saved[1], gamma, beta, g, scratch, n, h, w, _s())
     # pass 2: plain BN backward apply on the already masked gradient (in place: dy overwrites g)
@@ -225,29 +254,35 @@ def avgpool_bwd(dout, shape, out=None):
 
 
 # ------------------------------------------------------------------ head (fp32)
-def linear_fwd(x, w, bias=None, out=None):
-    """x [M,K] @ w[N,K]^T (+ bias)."""
+def _sgemm(a, b, c, bias, m, n, k, sam, sak, sbk, sbn, ldc, accumulate, ws):
+    need = _lib.call("peclr_sgemm_workspace_bytes", m, n, k)
+    buf, nbytes = (ws or _default_ws("sgemm", zero=True)).get(need, a.device)
+    _lib.call("peclr_sgemm", a, b, c, bias, m, n, k, sam, sak, sbk, sbn, ldc, accumulate, buf, nbytes, _s())
+
+
+def linear_fwd(x, w, bias=None, out=None, ws=None):
+    """x [M,K] @ w[N,K]^T (+ bias).  ws: zero-initialised Workspace of the split-K partials (shared by the head)."""
     m, k = x.shape
     n = w.shape[0]
     out = out if out is not None else torch.empty((m, n), dtype=torch.float32, device=x.device)
-    _lib.call("peclr_sgemm", x, w, out, bias, m, n, k, k, 1, 1, k, n, 0, _s())
+    _sgemm(x, w, out, bias, m, n, k, k, 1, 1, k, n, 0, ws)
     return out
 
 
-def linear_dgrad(dy, w, out=None):
+def linear_dgrad(dy, w, out=None, ws=None):
     """dy [M,N] @ w [N,K] -> [M,K]."""
     m, n = dy.shape
     k = w.shape[1]
     out = out if out is not None else torch.empty((m, k), dtype=torch.float32, device=dy.device)
-    _lib.call("peclr_sgemm", dy, w, out, None, m, k, n, n, 1, k, 1, k, 0, _s())
+    _sgemm(dy, w, out, None, m, k, n, n, 1, k, 1, k, 0, ws)
     return out
 
 
-def linear_wgrad(dy, x, dw):
+def linear_wgrad(dy, x, dw, ws=None):
     """dw [N,K] += dy[M,N]^T @ x[M,K]."""
     m, n = dy.shape
     k = x.shape[1]
-    _lib.call("peclr_sgemm", dy, x, dw, None, n, k, m, 1, n, k, 1, k, 1, _s())
+    _sgemm(dy, x, dw, None, n, k, m, 1, n, k, 1, k, 1, ws)
     return dw
 
 
@@ -388,7 +423,7 @@ def build_opt_tables(seg_sizes, seg_wd, device):
         seg_wd=torch.tensor(np.asarray(seg_wd, dtype=np.float32), device=device),
         chunk_seg=torch.tensor(np.asarray(cseg, dtype=np.int32), device=device),
         chunk_begin=torch.tensor(np.asarray(cbeg, dtype=np.int64), device=device),
-        norms=torch.zeros(2 * len(seg_sizes), dtype=torch.float32, device=device),
+        norms=torch.zeros(2 * len(seg_sizes), dtype=torch.float64, device=device),
         num_segs=len(seg_sizes), num_chunks=len(cseg),
     )
 

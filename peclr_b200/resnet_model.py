@@ -109,16 +109,37 @@ class ResNetModel(nn.Module):
     def _init_like_reference(self, pretrained):
         """Same initial values (and RNG consumption) as the reference: a torchvision ResNet built on the CPU,
         then final_layer's default nn.Linear init (resnet_model.py:13-29).  ImageNet weights cannot be
-        downloaded here; `pretrained` loads them only from $PECLR_PRETRAINED_DIR/<arch>.pth if present."""
+        downloaded here (no network): `pretrained` loads them from $PECLR_PRETRAINED_DIR/<arch>.pth.  The reference's
+        BaseModel hard-codes pretrained=True (base_model.py:23), i.e. it ALWAYS starts from ImageNet weights; when
+        the file is missing this build says so loudly (a warning on stderr and through `warnings`) instead of
+        silently training from a different starting point, or raises if PECLR_REQUIRE_PRETRAINED=1.  The source of
+        the initial weights is kept in `self.init_source` (the trainer logs it and stores it in checkpoints)."""
         import os
+        import sys
+        import warnings
 
         import torchvision
 
         tv = getattr(torchvision.models, self.arch)(weights=None, norm_layer=nn.BatchNorm2d)
+        self.init_source = "random (torchvision default init)"
         if pretrained:
-            path = os.path.join(os.environ.get("PECLR_PRETRAINED_DIR", ""), self.arch + ".pth")
+            root = os.environ.get("PECLR_PRETRAINED_DIR", "")
+            path = os.path.join(root, self.arch + ".pth")
             if os.path.isfile(path):
                 tv.load_state_dict(torch.load(path, map_location="cpu"))
+                self.init_source = "imagenet:" + path
+            elif os.environ.get("PECLR_REQUIRE_PRETRAINED", "0") == "1":
+                raise FileNotFoundError(
+                    f"pretrained=True (as the reference hard-codes) but {path!r} does not exist; put the torchvision "
+                    f"{self.arch} ImageNet state_dict there (set PECLR_PRETRAINED_DIR), or unset "
+                    "PECLR_REQUIRE_PRETRAINED to accept random initialisation")
+            elif os.environ.get("PECLR_ALLOW_RANDOM_INIT", "0") != "1":
+                msg = (f"peclr_b200: pretrained=True but no ImageNet weights at {path!r} (PECLR_PRETRAINED_DIR="
+                       f"{root!r}): the encoder starts from RANDOM initialisation, unlike the reference, which "
+                       "downloads torchvision's ImageNet weights.  Set PECLR_ALLOW_RANDOM_INIT=1 to silence this, "
+                       "PECLR_REQUIRE_PRETRAINED=1 to make it an error.")
+                warnings.warn(msg, RuntimeWarning, stacklevel=3)
+                print("WARNING: " + msg, file=sys.stderr)
         self.final_layer = nn.Sequential(nn.Linear(tv.fc.in_features, 21 * 3 + 1))
         tv_sd = [(k, v) for k, v in tv.state_dict().items() if not k.startswith("fc.")]
         own = self.features.state_dict()

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     lib = ctypes.CDLL(lib_path)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.peclr_abi_version() == 2
+    assert lib.peclr_abi_version() == 3
 
 
 def test_python_binding_matches_header(lib_path):
@@ -46,6 +46,22 @@ def test_python_binding_matches_header(lib_path):
         n = 0 if args in ("void", "") else len(args.split(","))
         assert n == len(argtypes), (name, n, len(argtypes))
     _lib.load()
+
+
+def test_workspace_queries_run_without_a_gpu(lib_path):
+    """The *_workspace_bytes entry points are host arithmetic (no launch): callable on the CPU-only build box."""
+    from peclr_b200 import _lib
+
+    # 56x56 64->64 3x3 at 2B = 256: few output tiles -> many pixel splits -> a workspace; 1 pixel chunk -> none
+    big = _lib.call("peclr_conv2d_wgrad_workspace_bytes", 256, 56, 56, 64, 64, 3, 1)
+    assert big > 0 and big % (64 * 9 * 64 * 4) == 0
+    assert _lib.call("peclr_conv2d_wgrad_workspace_bytes", 1, 8, 8, 64, 64, 1, 1) == 0
+    assert _lib.call("peclr_conv2d_wgrad_workspace_bytes", 4, 7, 7, 64, 64, 3, 2) < 0  # odd size at stride 2
+    assert _lib.call("peclr_stem_wgrad_workspace_bytes", 256, 224, 224) > 0
+    assert _lib.call("peclr_sgemm_workspace_bytes", 256, 512, 2048) > 256 * 512 * 4
+    assert _lib.call("peclr_sgemm_workspace_bytes", 4096, 4096, 64) == 0  # enough tiles: K is not split
+    small, large = (_lib.call("peclr_ntxent_workspace_bytes", b, w) for b, w in ((8, 1), (128, 8)))
+    assert 0 < small < large
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -255,3 +255,59 @@ def test_checkpoint_save_and_trainer_restore(model, tmp_path):
     assert float(other.engine.exp_avg[0]) == 0.125 and float(other.engine.exp_avg_sq[-1]) == 0.5
     assert tr2.lr_schedulers[0]["scheduler"].last_epoch == sch.last_epoch == 5
     assert tr2.optimizers[0].param_groups[0]["lr"] == pytest.approx(opt.param_groups[0]["lr"])
+
+
+def test_pretrained_without_weights_is_loud(monkeypatch, tmp_path, capsys):
+    """The reference hard-codes pretrained=True (base_model.py:23): a missing ImageNet file must not pass silently."""
+    from peclr_b200.easydict import EasyDict
+    from peclr_b200.model_utils import get_wrapper_model
+
+    cfg = EasyDict(dict(po.default_config(resnet_size="18", batch_size=2, num_samples=4)))
+    monkeypatch.setenv("PECLR_PRETRAINED_DIR", str(tmp_path))
+    monkeypatch.delenv("PECLR_ALLOW_RANDOM_INIT", raising=False)
+    monkeypatch.delenv("PECLR_REQUIRE_PRETRAINED", raising=False)
+    with pytest.warns(RuntimeWarning, match="RANDOM initialisation"):
+        enc = get_wrapper_model(cfg, pretrained=True)
+    assert "random" in enc.init_source and "RANDOM initialisation" in capsys.readouterr().err
+    monkeypatch.setenv("PECLR_REQUIRE_PRETRAINED", "1")
+    with pytest.raises(FileNotFoundError):
+        get_wrapper_model(cfg, pretrained=True)
+    # with the file in place the weights are loaded and the source recorded
+    import torchvision
+
+    monkeypatch.delenv("PECLR_REQUIRE_PRETRAINED")
+    tv = torchvision.models.resnet18(weights=None)
+    torch.save(tv.state_dict(), tmp_path / "resnet18.pth")
+    enc = get_wrapper_model(cfg, pretrained=True)
+    assert enc.init_source.startswith("imagenet:")
+    assert torch.equal(enc.features[0].weight, tv.conv1.weight)
+
+
+def test_trainer_steps_on_the_last_batch_of_a_partial_window():
+    """Lightning 1.0.8 applies the accumulated gradient on the final batch of an epoch even if the accumulation
+    window is not full: 5 batches at accumulate_grad_batches = 2 -> optimiser steps after batches 2, 4 and 5."""
+    from peclr_b200.lightning import Trainer
+
+    flags = [(i, last) for i, _, last in Trainer._with_last_flag(iter(range(5)), None)]
+    assert flags == [(0, False), (1, False), (2, False), (3, False), (4, True)]
+    acc = 2
+    assert [i + 1 for i, last in flags if (i + 1) % acc == 0 or last] == [2, 4, 5]
+    assert [(i, last) for i, _, last in Trainer._with_last_flag(iter(range(5)), 3)] == [(0, False), (1, False), (2, True)]
+    assert list(Trainer._with_last_flag(iter(()), None)) == []
+
+
+def test_model_checkpoint_restores_top_k_bookkeeping(tmp_path):
+    from peclr_b200.lightning import ModelCheckpoint
+
+    d = tmp_path / "checkpoints"
+    d.mkdir()
+    for e in (0, 3):
+        (d / f"epoch={e}.ckpt").write_bytes(b"x")
+    cb = ModelCheckpoint(save_top_k=2, dirpath=str(d))
+    rec = {"callbacks": {"ModelCheckpoint": {"best": [(0.5, str(d / "epoch=3.ckpt")), (0.9, str(d / "epoch=0.ckpt")),
+                                                      (0.7, str(d / "epoch=1.ckpt"))]}}}
+    cb.restore_state(rec, str(d / "epoch=3.ckpt"))
+    assert cb.best == [(0.5, str(d / "epoch=3.ckpt")), (0.9, str(d / "epoch=0.ckpt"))]  # the deleted file is dropped
+    cb2 = ModelCheckpoint(save_top_k=2, dirpath=str(d))
+    cb2.restore_state({}, str(d / "epoch=3.ckpt"))  # a checkpoint without the record (e.g. the reference's)
+    assert [p for _, p in cb2.best] == [str(d / "epoch=0.ckpt"), str(d / "epoch=3.ckpt")]
