@@ -2,11 +2,19 @@
 """Benchmark of the PeCLR pre-training step (BASELINE.json: two-view images/sec, ResNet-50, batch 128, 224^2).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model 50|152] [--batch B]
+                    [--accumulate A]
 
-ours       one process per GPU (torchrun for N > 1); a step = Hybrid2Model.training_step + backward + gradient
-           exchange + fused LARS-Adam step on one synthetic two-view batch.  Prints ONE JSON line (rank 0).
-reference  the reference's own CPU path (oracle port of Hybrid2Model.training_step / backward / LARS-Adam step;
-           the reference is Python and cannot travel to the GPU box) on all host cores, bounded sample per step.
+ours       one process per GPU (torchrun for N > 1); a step = one OPTIMISER step: A micro-steps of
+           Hybrid2Model.training_step + backward (A = --accumulate, Lightning's accumulate_grad_batches; default 1),
+           then gradient exchange + fused LARS-Adam, each micro-step on its own synthetic two-view batch.  Prints ONE
+           JSON line (rank 0).  On the default workload (BASELINE config 2: ResNet-50, B = 128, 224^2) the line also
+           carries `secondary`: ResNet-152 B = 128 (config 4) and ResNet-152 B = 64 x accumulate 16 (config 5, the
+           paper's recipe), measured the same way in the same process, and for N > 1 `parity`: the multi-GPU parity
+           checks of scripts/dist_check.py run before the timed region (a failing check exits non-zero).
+reference  the reference's own CPU path on all host cores, bounded sample per step: the reference's Hybrid2Model
+           imported from /root/reference where that exists (build container; kind "reference"), else its oracle port
+           (oracle/peclr_oracle.py, bit-identical to the executed reference -- tests/test_oracle_vs_reference.py; the
+           reference is a Python tree that cannot travel to the GPU box; kind "port").
 """
 import argparse
 import json
@@ -21,6 +29,9 @@ sys.path.insert(0, ROOT)
 
 # conv-only training FLOPs per image, 2*(3*MAC_fwd - MAC_conv1)
 F_TRAIN = {("50", 224): 24.287e9, ("152", 224): 68.834e9, ("50", 64): 1.983e9, ("50", 128): 7.930e9}
+CONV_CALLS = {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_dgrad_bnreduce", "peclr_conv2d_wgrad",
+              "peclr_stem_fprop", "peclr_stem_wgrad"}
+CPU_SAMPLE_PAIRS = 32  # per-step sample of BOTH CPU legs (cpu_baseline and --impl reference), scaled per image
 
 
 def peaks():
@@ -31,16 +42,25 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-def ncu_traffic(args):
-    """dram__bytes_read + dram__bytes_write per conv_gemm_kernel launch (average over the launches of one step),
-    from the committed ncu capture (profiles/roofline_r01.json, taken on the default ResNet-50 workload); None for
-    any other workload or if the capture is missing."""
-    if (args.model, args.batch, args.size) != ("50", 128, 224):
-        return None
+def lib_digest():
+    """Digest of the CUDA sources + flags the loaded library was built from (peclr_b200/build.py stamp)."""
     try:
-        return int(json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))["dram_bytes_per_launch"])
-    except Exception:
+        return open(os.path.join(ROOT, "peclr_b200", "csrc", ".build_stamp")).read().strip()[:16]
+    except OSError:
         return None
+
+
+def ncu_traffic(model, batch, size):
+    """dram__bytes_read + dram__bytes_write per conv_gemm_kernel launch (average over the launches of one step) from
+    the committed ncu launch list -- used ONLY if that capture was taken on the build now loaded (same source
+    digest) and on this workload; otherwise null (a stale constant would be worse than none)."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
+        if rec.get("lib_digest") == lib_digest() and rec.get("workload") == [model, batch, size]:
+            return int(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -78,17 +98,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def build_config(args, world):
+def build_config(model, batch, accumulate, world):
     from peclr_b200.easydict import EasyDict
 
-    return EasyDict(batch_size=args.batch, lr=1e-4, opt_weight_decay=1e-6, output_dim=128,
+    return EasyDict(batch_size=batch, lr=1e-4, opt_weight_decay=1e-6, output_dim=128,
                     projection_head_hidden_dim=512, projection_head_input_dim=2048, warmup_epochs=10,
-                    num_of_mini_batch=1, augmentation=["crop", "rotate"], optimizer="LARS",
-                    resnet_size=args.model, num_samples=args.batch * world * 1000)
+                    num_of_mini_batch=accumulate, augmentation=["crop", "rotate"], optimizer="LARS",
+                    resnet_size=model, num_samples=batch * world * accumulate * 1000)
+
+
+def workload_name(model, batch, size, accumulate):
+    acc = ", accumulate_grad_batches %d (one optimiser step per %d micro-batches)" % (accumulate, accumulate) \
+        if accumulate > 1 else ""
+    return ("ResNet-%s PeCLR step, per-GPU batch %d (2x%d images), %dx%d synthetic two-view, crop+rotate "
+            "equivariance, NT-Xent over the global batch, LARS-Adam%s" % (model, batch, batch, size, size, acc))
 
 
 # ---------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
+def measure(ctx, model_size, batch, size, accumulate, steps, warmup, sample_clocks=False, profile=True,
+            ncu_step=False, no_graph=False):
+    """Builds the model, times `steps` optimiser steps device-resident and end to end, profiles the conv launches of
+    one micro-step.  Returns a dict (rank 0: complete; other ranks: partial)."""
     import torch
     import torch.distributed as dist
 
@@ -97,18 +127,9 @@ def run_ours(args):
     from peclr_b200.lightning import seed_everything
     from peclr_b200.synthetic import synthetic_batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
     seed_everything(5)
-    cfg = build_config(args, world)
+    cfg = build_config(model_size, batch, accumulate, world)
     model = Hybrid2Model(cfg)
     model.cuda()
 
@@ -122,73 +143,84 @@ def run_ours(args):
     sched = sch["scheduler"]
     model.train()
 
-    # two distinct host batches (pinned) so consecutive steps never see the same input
-    host = [synthetic_batch(args.batch, args.size, seed=5 + 17 * rank + i, structured=False, pin_memory=True)
-            for i in range(2)]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    # distinct host batches (pinned): consecutive micro-steps never see the same input
+    n_host = 2 if accumulate == 1 else min(accumulate, 4)
+    host = [synthetic_batch(batch, size, seed=5 + 17 * rank + i, structured=False, pin_memory=True)
+            for i in range(n_host)]
+    micro_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    scale = 1.0 / accumulate
 
-    def eager_step(batch):
-        opt.zero_grad()
-        out = model.training_step(batch, 0)
-        out["loss"].backward()
-        model.sync_gradients()
-        opt.step()
-        sched.step()
+    def eager_micro(mb):
+        out = model.training_step(mb, 0)
+        (out["loss"] * scale).backward() if accumulate > 1 else out["loss"].backward()
         return out["loss"]
 
     graphed = None
-    if not args.no_graph:
+    if not no_graph:
         from peclr_b200.graphed import GraphedStep
 
-        graphed = GraphedStep(model, resident[0], grad_scale=1.0)
+        graphed = GraphedStep(model, resident[0], grad_scale=scale)
 
-    def step(batch):
-        """One optimiser step.  With the CUDA graph, training_step + backward are replayed from the capture
-        (same kernels, one submission); gradient exchange and the fused optimiser run after it."""
-        if graphed is None:
-            return eager_step(batch)
+    def step(get_batch, after_micro=None):
+        """One optimiser step = `accumulate` micro-steps (training_step + backward; with the CUDA graph replayed
+        from the capture: same kernels, one submission each), then gradient exchange + the fused optimiser."""
         opt.zero_grad()
-        out = graphed(batch)
+        for j in range(accumulate):
+            mb = get_batch(j)
+            loss = graphed(mb)["loss"] if graphed is not None else eager_micro(mb)
+            if after_micro is not None:
+                after_micro(j, loss)
         model.sync_gradients()
         opt.step()
         sched.step()
-        return out["loss"]
+        return loss
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing ------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step(resident[i % 2])
+    ctr = [0]
+
+    def next_resident(_):
+        ctr[0] += 1
+        return resident[ctr[0] % n_host]
+
+    for _ in range(warmup):
+        step(next_resident)
     barrier()
-    if args.ncu_step:
+    if ncu_step:
         # launch-list capture: `ncu --profile-from-start off ... bench.py --ncu-step --no-graph` sees exactly the
         # launches of ONE step (cudaProfilerStart/Stop); nothing printed under a profiler is a bench value
         torch.cuda.profiler.start()
-        step(resident[0])
+        step(next_resident)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        return
+        return None
     launches0 = _lib.LAUNCHES
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(ctx["local"])
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        loss = step(resident[i % 2])
+    for _ in range(steps):
+        loss = step(next_resident)
     ev1.record()
     barrier()
-    sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
+    if sampler is not None:
+        sampler.stop_flag = True
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = _lib.LAUNCHES - launches0
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    images = 2 * args.batch * world * args.steps
+    images = 2 * batch * accumulate * world * steps
     value = images / (ms / 1e3)
     final_loss = float(loss.item())
 
@@ -203,95 +235,182 @@ def run_ours(args):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            for k, v in host[i % 2].items():
+            for k, v in host[i % n_host].items():
                 staged[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
+        total = n * accumulate
+        cur = torch.cuda.current_stream()
         for s in range(2):
-            consumed[s].record(torch.cuda.current_stream())
+            consumed[s].record(cur)
         stage(0)
-        for i in range(n):
-            if i + 1 < n:
-                stage(i + 1)
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            l = step(staged[i % 2])
-            consumed[i % 2].record(torch.cuda.current_stream())
-            loss_host.copy_(l.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        it = [0]
 
-    e2e_run(max(3, args.warmup))
+        def get(_):
+            i = it[0]
+            if i + 1 < total:
+                stage(i + 1)
+            cur.wait_event(ready[i % 2])
+            return staged[i % 2]
+
+        def after(_, l):
+            i = it[0]
+            consumed[i % 2].record(cur)
+            loss_host.copy_(l.detach(), non_blocking=True)
+            it[0] = i + 1
+
+        for _ in range(n):
+            step(get, after)
+        cur.synchronize()
+
+    e2e_run(3 if accumulate == 1 else 1)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    e2e_run(args.steps)
+    e2e_run(steps)
     ev1.record()
     barrier()
     # the host is part of this path: take the larger of the device-event time and the wall clock
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = images / (float(t.item()) / 1e3)
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = images / (e2e_ms / 1e3)
 
-    # ---- dominant-kernel roofline: every tensor-core conv launch of ONE step bracketed by CUDA events ----
+    # ---- dominant-kernel roofline: every tensor-core conv launch of ONE micro-step bracketed by CUDA events ----
     roof = None
+    if profile:
+        # (a step is collective when world > 1 -- fused all-gather -- so every rank runs it)
+        opt.zero_grad()
+        prof = _lib.profile_calls(lambda: eager_micro(resident[0]), CONV_CALLS)
+        opt.zero_grad()
+        if rank == 0:
+            pk = peaks()
+            flops = {"gemm": 0.0, "wgrad": 0.0}
+            times = {"gemm": 0.0, "wgrad": 0.0}
+            for name, a, ms_k in prof:
+                kind = "wgrad" if "wgrad" in name else "gemm"
+                flops[kind] += conv_flops(name, a)
+                times[kind] += ms_k
+            ach = flops["gemm"] / (times["gemm"] * 1e-3) / 1e12 if times["gemm"] > 0 else 0.0
+            ach_w = flops["wgrad"] / (times["wgrad"] * 1e-3) / 1e12 if times["wgrad"] > 0 else 0.0
+            f_train = F_TRAIN.get((model_size, size))
+            roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM fprop+dgrad)",
+                    "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(model_size, batch, size),
+                    "peak_source": pk["src"] + " (sustained)",
+                    "kernel_ms_per_micro_step": round(times["gemm"], 3),
+                    "wgrad_kernel": {"achieved": round(ach_w, 1), "frac": round(ach_w / pk["tf_sustained"], 4),
+                                     "kernel_ms_per_micro_step": round(times["wgrad"], 3),
+                                     "note": "incl. the ordered reduction of the pixel splits"},
+                    "step_conv_flop_frac": round(value * f_train / world / (pk["tf_sustained"] * 1e12), 4)
+                    if f_train else None}
+            try:  # (explanatory extra: never let it take the bench line down)
+                roof["per_launch_roofline"] = launch_bound_fraction(prof, pk["tf_sustained"], pk["hbm"])
+            except Exception as exc:  # pragma: no cover
+                roof["per_launch_roofline"] = {"error": repr(exc)}
+    res = {"value": round(value, 1), "ms_per_step": round(ms / steps, 3), "steps": steps, "warmup": warmup,
+           "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": micro_bytes * accumulate,
+                   "d2h_bytes_per_step": 4 * accumulate},
+           "gpu_launches": int(launches), "roofline": roof, "final_loss": final_loss,
+           "clocks": sampler.summary() if sampler is not None else None, "micro_bytes": micro_bytes,
+           "kernels_per_micro_step": graphed.kernels_per_replay if graphed is not None else None}
+    del graphed, model, opt, sched, staged, resident, host
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.setdefault("PECLR_ALLOW_RANDOM_INIT", "1")  # synthetic benchmark: random init is the stated workload
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = dict(world=world, rank=rank, local=local, dev=dev)
+
+    # ---- multi-GPU parity BEFORE anything is timed (scripts/dist_check.py; the oracle is the checker) ----------
+    parity = None
+    if world > 1 and not args.no_parity and not args.ncu_step:
+        from peclr_b200.hybrid2_model import Hybrid2Model
+        from scripts import dist_check
+
+        pcfg = build_config("18", args.batch, 1, world)  # (a small trunk: only its engine's loss path is used)
+        pcfg.projection_head_input_dim = 512
+        probe = Hybrid2Model(pcfg).cuda()
+        probe.engine.world, probe.engine.rank = world, rank
+        parity = dist_check.run_all(probe.engine, args.batch, world, rank, dev)
+        del probe
+        torch.cuda.empty_cache()
+        if not parity["pass"]:
+            if rank == 0:
+                print(json.dumps({"parity": parity, "error": "multi-GPU parity check failed"}))
+            dist.destroy_process_group()
+            raise SystemExit(3)
+
+    main_res = measure(ctx, args.model, args.batch, args.size, args.accumulate, args.steps, args.warmup,
+                       sample_clocks=True, ncu_step=args.ncu_step, no_graph=args.no_graph)
+    if args.ncu_step:
+        return
+    default_workload = (args.model, args.batch, args.size, args.accumulate) == ("50", 128, 224, 1)
+    secondary = None
+    if default_workload and not args.no_secondary:
+        secondary = {}
+        s152 = max(5, args.steps // 5)
+        r = measure(ctx, "152", 128, 224, 1, s152, 3)
+        secondary["rn152_bs128"] = dict(config={"workload": workload_name("152", 128, 224, 1),
+                                                "baseline_config": "BASELINE.json configs[3] (per GPU)"}, **_slim(r))
+        s5 = max(2, args.steps // 12)
+        r = measure(ctx, "152", 64, 224, 16, s5, 1)
+        secondary["rn152_bs64_acc16"] = dict(config={"workload": workload_name("152", 64, 224, 16),
+                                                     "baseline_config": "BASELINE.json configs[4] (per GPU)"},
+                                             **_slim(r))
     cpu = None
-    # (a step is collective when world > 1 -- fused all-gather, gradient all-reduce -- so every rank runs it)
-    prof = _lib.profile_calls(lambda: eager_step(resident[0]),
-                              {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_dgrad_bnreduce",
-                               "peclr_conv2d_wgrad", "peclr_stem_fprop", "peclr_stem_wgrad"})
-    if rank == 0:
-        pk = peaks()
-        flops = {"gemm": 0.0, "wgrad": 0.0}
-        times = {"gemm": 0.0, "wgrad": 0.0}
-        for name, a, ms_k in prof:
-            kind = "wgrad" if "wgrad" in name else "gemm"
-            flops[kind] += conv_flops(name, a)
-            times[kind] += ms_k
-        ach = flops["gemm"] / (times["gemm"] * 1e-3) / 1e12 if times["gemm"] > 0 else 0.0
-        ach_w = flops["wgrad"] / (times["wgrad"] * 1e-3) / 1e12 if times["wgrad"] > 0 else 0.0
-        f_train = F_TRAIN.get((args.model, args.size))
-        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM fprop+dgrad)",
-                "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(args),
-                "peak_source": pk["src"] + " (sustained)",
-                "kernel_ms_per_step": round(times["gemm"], 3),
-                "wgrad_kernel": {"achieved": round(ach_w, 1), "frac": round(ach_w / pk["tf_sustained"], 4),
-                                 "kernel_ms_per_step": round(times["wgrad"], 3)},
-                "step_conv_flop_frac": round(value * f_train / world / (pk["tf_sustained"] * 1e12), 4) if f_train else None}
-        try:  # (explanatory extra: never let it take the bench line down)
-            roof["per_launch_roofline"] = launch_bound_fraction(prof, pk["tf_sustained"], pk["hbm"])
-        except Exception as exc:  # pragma: no cover
-            roof["per_launch_roofline"] = {"error": repr(exc)}
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(args, budget_s=20.0)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, budget_s=20.0)
     if world > 1:
         dist.barrier()
     if rank == 0:
         line = {
             "metric": "two-view images/sec, PeCLR pre-training step (fwd+bwd+LARS-Adam), ResNet-%s bs%d %dx%d"
                       % (args.model, args.batch, args.size, args.size),
-            "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ResNet-%s PeCLR step, per-GPU batch %d (2x%d images), %dx%d synthetic two-view, "
-                                   "crop+rotate equivariance, NT-Xent over the global batch, LARS-Adam"
-                                   % (args.model, args.batch, args.batch, args.size, args.size),
+            "value": main_res["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args.model, args.batch, args.size, args.accumulate),
                        "global_batch": args.batch * world, "parallelism": "dp%d" % world,
-                       "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2; no explicit flush"
-                             % (h2d_bytes / 1e6)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-            "roofline": roof,
+                       "l2": "inputs (%.0f MB/micro-step) and activations exceed the 126 MB L2; no explicit flush"
+                             % (main_res["micro_bytes"] / 1e6),
+                       "init": "random (torchvision default init; no network for ImageNet weights)"},
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"],
+            "clocks": main_res["clocks"],
+            "roofline": main_res["roofline"],
             "cpu_baseline": cpu,
-            "final_loss": final_loss,
+            "final_loss": main_res["final_loss"],
+            "lib_digest": lib_digest(),
         }
+        if secondary is not None:
+            line["secondary"] = secondary
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _slim(r):
+    roof = r["roofline"] or {}
+    return {"value": r["value"], "unit": "images/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+            "warmup": r["warmup"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "final_loss": r["final_loss"],
+            "roofline": {k: roof.get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac",
+                                                  "step_conv_flop_frac", "wgrad_kernel")}}
 
 
 def conv_bytes(name, a):
@@ -341,76 +460,102 @@ def conv_flops(name, a):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
-def _oracle_model(args, batch):
+def _cpu_model(args, batch):
+    """The reference's own Hybrid2Model (imported from /root/reference through oracle/ref_shims.py) where the reference
+    tree exists -- this build container --, else its oracle port (the GPU box has no /root/reference)."""
     import torch
 
     from oracle import peclr_oracle as po
+    from oracle import ref_shims
 
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = po.default_config(resnet_size=args.model, batch_size=batch, num_samples=batch * 1000)
+    cfg = po.default_config(resnet_size=args.model, batch_size=batch, num_samples=batch * 1000,
+                            num_of_mini_batch=args.accumulate)
     torch.manual_seed(5)
-    model = po.OracleHybrid2Model(cfg)
+    kind = "port"
+    model = None
+    if ref_shims.reference_available() and not os.environ.get("PECLR_BENCH_FORCE_PORT"):
+        try:
+            ref = ref_shims.load_reference()
+            model = ref.Hybrid2Model(ref.EasyDict(dict(cfg)))
+            kind = "reference"
+        except Exception:  # pragma: no cover  (fall back to the port rather than lose the bench line)
+            model = None
+    if model is None:
+        model = po.OracleHybrid2Model(cfg)
     model.trainer = po._TrainerStub(world_size=1, max_epochs=100)
     model.setup("fit")
     (opt,), (sch,) = model.configure_optimizers()
-    return po, model, opt, sch["scheduler"]
+    return po, model, opt, sch["scheduler"], kind
 
 
-def _time_oracle_steps(args, batch, warm, steps):
-    po, model, opt, sched = _oracle_model(args, batch)
+def _time_cpu_steps(args, batch, warm, steps):
+    po, model, opt, sched, kind = _cpu_model(args, batch)
     data = po.synthetic_batch(batch, args.size, seed=5, structured=False)
     for _ in range(warm):
         po.oracle_step(model, data, opt, sched)
     t0 = time.perf_counter()
     for _ in range(steps):
         po.oracle_step(model, data, opt, sched)
-    return (time.perf_counter() - t0) / steps
+    return (time.perf_counter() - t0) / steps, kind
 
 
-def pick_sample_batch(args, target_s=2.5):
-    """Largest per-step sample (pairs) whose step takes about target_s on this host."""
-    t4 = _time_oracle_steps(args, 4, 1, 1)
-    b = 4
-    while b * 2 <= args.batch and t4 * (b * 2 / 4) <= target_s:
-        b *= 2
-    return b
+def cpu_sample_pairs(args):
+    """Both CPU legs use the SAME per-step sample: min(B, 32) pairs of the B-pair batch (a full ResNet-50 B = 128 step
+    at 224^2 takes ~35 s on 8 cores: SURVEY 6), throughput scaled per image."""
+    return min(args.batch, CPU_SAMPLE_PAIRS)
+
+
+def _cpu_what(kind):
+    return ("the reference's Hybrid2Model.training_step + backward + LARSWrapper(Adam).step imported from "
+            "/root/reference" if kind == "reference" else
+            "oracle port of the reference's Hybrid2Model.training_step + backward + LARSWrapper(Adam).step")
 
 
 def cpu_baseline(args, budget_s=20.0):
-    b = pick_sample_batch(args, target_s=budget_s / 4)
-    dt = _time_oracle_steps(args, b, 1, 2)
-    return {"value": round(2 * b / dt, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle port of the reference step (fp32, torch CPU, %d threads): 1 warm-up + 2 timed steps at "
-                      "B=%d of %d pairs, %dx%d, scaled per image" % (os.cpu_count(), b, args.batch, args.size, args.size)}
+    b = cpu_sample_pairs(args)
+    dt, kind = _time_cpu_steps(args, b, 1, 2)
+    return {"value": round(2 * b / dt, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": "%s (fp32, torch CPU, %d threads): 1 warm-up + 2 timed steps at B=%d of %d pairs, %dx%d, "
+                      "scaled per image" % (_cpu_what(kind), os.cpu_count(), b, args.batch, args.size, args.size)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step so that the whole --steps K --warmup W run stays within ~2 minutes of CPU work
-    b = pick_sample_batch(args, target_s=min(2.5, 120.0 / max(1, args.steps + args.warmup)))
-    po, model, opt, sched = _oracle_model(args, b)
+    b = cpu_sample_pairs(args)
+    po, model, opt, sched, kind = _cpu_model(args, b)
     data = po.synthetic_batch(b, args.size, seed=5, structured=False)
-    for _ in range(args.warmup):
+    # bounded run: at most ~3 minutes of CPU work whatever --steps / --warmup ask for (the count actually timed is
+    # reported in "steps")
+    t_probe = time.perf_counter()
+    po.oracle_step(model, data, opt, sched)
+    probe = time.perf_counter() - t_probe
+    budget = max(1, int(150.0 / max(probe, 1e-3)))
+    warm = min(args.warmup, max(0, budget // 4))
+    steps = max(1, min(args.steps, budget - warm))
+    for _ in range(warm):
         po.oracle_step(model, data, opt, sched)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         po.oracle_step(model, data, opt, sched)
-    dt = (time.perf_counter() - t0) / args.steps
+    dt = (time.perf_counter() - t0) / steps
     value = round(2 * b / dt, 2)
-    sample = ("oracle port of the reference's Hybrid2Model.training_step + backward + LARSWrapper(Adam).step (fp32, "
-              "torch CPU, %d threads); each step = B=%d pairs of the %d-pair batch, %dx%d, throughput per image"
-              % (os.cpu_count(), b, args.batch, args.size, args.size))
+    sample = ("%s (fp32, torch CPU, %d threads); each step = B=%d pairs of the %d-pair batch, %dx%d, throughput per "
+              "image; %d of the requested %d steps timed (bounded run)"
+              % (_cpu_what(kind), os.cpu_count(), b, args.batch, args.size, args.size, steps, args.steps))
     print(json.dumps({
         "impl": "reference",
         "metric": "two-view images/sec, PeCLR pre-training step (fwd+bwd+LARS-Adam), ResNet-%s bs%d %dx%d"
                   % (args.model, args.batch, args.size, args.size),
-        "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ResNet-%s PeCLR step on host cores, bounded sample B=%d pairs per step" % (args.model, b)},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": {"workload": "ResNet-%s PeCLR step on host cores, bounded sample B=%d pairs per step of the %d-pair "
+                               "batch, %dx%d" % (args.model, b, args.batch, args.size, args.size),
+                   "sample_pairs_per_step": b},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -424,7 +569,13 @@ def main():
     ap.add_argument("--model", default="50", choices=["18", "34", "50", "101", "152"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--accumulate", type=int, default=1,
+                    help="accumulate_grad_batches: micro-steps per optimiser step (BASELINE config 5: 16)")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-secondary", dest="no_secondary", action="store_true",
+                    help="skip the ResNet-152 blocks (configs 4 / 5) the default workload also measures")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true",
+                    help="skip the multi-GPU parity checks run before the timed region at world > 1")
     ap.add_argument("--ncu-step", dest="ncu_step", action="store_true",
                     help="run the warm-up, then ONE step between cudaProfilerStart/Stop, and exit (for ncu)")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="submit kernels eagerly (no CUDA graph)")

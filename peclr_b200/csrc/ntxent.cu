@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) ntxent_fused_kernel(const NtxentArgs a
       }
     }
     if (blockIdx.x == 0 && threadIdx.x < 16 && a.stats)  // (P1's sums were complete at the first grid barrier)
-      a.stats[threadIdx.x] = (float)(a.acc[1 + threadIdx.x] / (double)a.B);
+      a.stats[threadIdx.x] = (float)(__ldcg(a.acc + 1 + threadIdx.x) / (double)a.B);
   }
   if (!a.g_p) return;
   const int gz_chunks = (n_glob + a.col_chunk - 1) / a.col_chunk;

@@ -3,10 +3,11 @@
 CPU oracle on identical weights and batch.
 
 Tolerances (SURVEY.md 3.6 / 8(d)(iii), bf16 tensor-core trunk, errors vs the fp32 oracle from an
-oracle-warm-started state): |dloss| <= 1.5e-3 (+ the envelope measured in the same run), global gradient
-cosine >= 0.93, layer4 + head cosine >= 0.985 -- i.e. within 1.5x of what the reference itself does under
-torch bf16 autocast, which is measured alongside and printed.  At default init only the loss is compared
-(the gradients of ANY 16-bit trunk are uncorrelated with fp64 there).
+oracle-warm-started state), FIXED: |dloss| <= 1.5e-3, global gradient cosine >= 0.93, layer4 + head cosine >=
+0.985 (tests/parity_util.py).  What the reference itself does under torch bf16 autocast on the same weights / batch
+is measured alongside and printed for context; it does not enter any assertion.  At default init only the loss is
+compared (the gradients of ANY 16-bit trunk are uncorrelated with fp64 there).  The step is bit-reproducible: two
+runs give identical loss, gradients and updated weights (no floating-point atomics anywhere, ABI 3).
 """
 import copy
 import os
@@ -17,6 +18,7 @@ import pytest
 import torch
 
 from oracle import peclr_oracle as po
+from parity_util import TOL_COS_ALL, TOL_COS_TOP, TOL_DLOSS, cos, grads_by_group
 
 pytestmark = pytest.mark.gpu
 
@@ -44,27 +46,6 @@ def make_pair(warm_steps):
     ours.load_state_dict(oracle.state_dict())
     ours.cuda()
     return cfg, oracle, ours
-
-
-def group_of(name):
-    if name.startswith("projection_head"):
-        return "head"
-    idx = name.split(".")[2]
-    return {"0": "stem", "1": "stem", "4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}[idx]
-
-
-def cos(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
-    return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-300))
-
-
-def grads_by_group(named):
-    out = {}
-    for n, g in named.items():
-        out.setdefault(group_of(n), []).append(g.detach().double().flatten().cpu())
-    out = {k: torch.cat(v) for k, v in out.items()}
-    out["all"] = torch.cat(list(out.values()))
-    return out
 
 
 @pytest.fixture(scope="module")
@@ -115,13 +96,58 @@ def test_step_loss_stats_grads_vs_oracle(warm):
         print("  %-7s |g| %.3e  cos ours %.4f  autocast-reference %.4f  rel-L2 ours %.3f" %
               (k, float(ref[k].norm()), got_cos[k], env_cos[k], rel))
     assert set(out) == set(out_o) and len(out) == 17
-    assert dloss <= 1.5e-3 + 1.5 * env_dloss
+    assert dloss <= TOL_DLOSS, dloss
     for k in out_o:
         if k != "loss":
             assert abs(out[k].item() - out_o[k].item()) <= 3e-2 * (abs(out_o[k].item()) + 0.05), k
-    assert got_cos["all"] >= min(0.93, env_cos["all"] - 0.03)
-    assert got_cos["layer4"] >= min(0.985, env_cos["layer4"] - 0.01)
-    assert got_cos["head"] >= min(0.985, env_cos["head"] - 0.01)
+    assert got_cos["all"] >= TOL_COS_ALL, got_cos
+    assert got_cos["layer4"] >= TOL_COS_TOP and got_cos["head"] >= TOL_COS_TOP, got_cos
+
+
+def test_step_is_bit_reproducible(warm):
+    """Same weights, same batch, three runs (eager, eager, CUDA-graph replay): identical loss, statistics, gradients;
+    and the optimiser step that follows gives identical weights."""
+    from peclr_b200.graphed import GraphedStep
+
+    cfg, oracle, ours = warm
+    sd = {k: v.clone() for k, v in ours.state_dict().items()}
+    batch = {k: v.cuda() for k, v in po.synthetic_batch(B, SIZE, seed=5).items()}
+
+    class T:
+        world_size, max_epochs = 1, 100
+
+    def run(graphed=None):
+        ours.load_state_dict(sd)
+        ours.trainer = T()
+        ours.setup("fit")
+        (opt,), (sch,) = ours.configure_optimizers()
+        ours.engine.exp_avg = ours.engine.exp_avg_sq = None
+        for _ in range(3):
+            sch["scheduler"].step()
+        ours.train()
+        opt.zero_grad()
+        if graphed is None:
+            out = ours.training_step(batch, 0)
+            out["loss"].backward()
+        else:
+            out = graphed(batch)
+        torch.cuda.synchronize()
+        grads = ours.engine.grads.clone()
+        opt.step()
+        torch.cuda.synchronize()
+        return {k: v.detach().clone() for k, v in out.items()}, grads, ours.engine.flat.clone()
+
+    o1, g1, w1 = run()
+    o2, g2, w2 = run()
+    assert all(torch.equal(o1[k], o2[k]) for k in o1), {k: (float(o1[k]), float(o2[k])) for k in o1}
+    assert torch.equal(g1, g2) and torch.equal(w1, w2)
+    assert float(g1.abs().max()) > 0 and not torch.equal(w1, ours.engine.flat * 0)
+    ours.load_state_dict(sd)
+    graphed = GraphedStep(ours, batch, grad_scale=1.0)
+    o3, g3, w3 = run(graphed)
+    assert all(torch.equal(o1[k], o3[k]) for k in o1)
+    assert torch.equal(g1, g3) and torch.equal(w1, w3)
+    ours.load_state_dict(sd)
 
 
 def test_optimizer_step_and_schedule_vs_oracle(warm):
