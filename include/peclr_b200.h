@@ -198,6 +198,16 @@ int peclr_weight_transpose(const float* src_flat, void* dst_bf16, const void* ta
 int peclr_stem_pack(const float* w, void* wpack, void* stream);
 int peclr_stem_unpack_grad(const float* gpack, float* g, void* stream);
 
+/* ---- downstream consumer of the exported encoder (csrc/rn25d_head.cu): the head of RN_25D_wMLPref
+ * (reference src/models/rn_25D_wMLPref.py:75-134 forward after the backbone, :6-72 ZrootMLP_ref), inference only
+ * (eval-mode BatchNorm1d).  out [B][64] = backbone output (fc of the ResNet trunk: peclr_sgemm on the pooled
+ * features); K [nK][3][3] camera matrices, nK = 1 (shared) or B.  `mlp` is a HOST array of 14 device pointers:
+ * {W1[128][64], b1, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, W2[128][128], b2, bn2.weight, bn2.bias,
+ * bn2.running_mean, bn2.running_var, W3[1][128], b3[1]}.  Outputs: kp3d [B][21][3], zrel [B][21][1], kp2d [B][21][2],
+ * kp25d [B][21][3] (zrel of the root joint zeroed, as the reference writes it through its views). */
+int peclr_rn25d_head(const float* out, const float* K, int nK, int B, const float* const* mlp, float bn_eps,
+                     float leaky_slope, float* kp3d, float* zrel, float* kp2d, float* kp25d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ SIGNATURES = {
     "peclr_weight_transpose": [P, P, P, I, I, P],
     "peclr_stem_pack": [P, P, P],
     "peclr_stem_unpack_grad": [P, P, P],
+    "peclr_rn25d_head": [P, P, I, I, P, F, F, P, P, P, P, P],
 }
 _RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong, "peclr_conv2d_wgrad_workspace_bytes": c_longlong,
              "peclr_stem_wgrad_workspace_bytes": c_longlong, "peclr_sgemm_workspace_bytes": c_longlong}

@@ -19,6 +19,9 @@ class FusedLARSAdam(torch.optim.Optimizer):
         self.lars, self.eta, self.clip, self.lars_eps = lars, eta, clip, lars_eps
         self.step_count = 0
         self._tables = None
+        # a new optimiser starts from fresh Adam moments (they live in the engine's flat buffers; load_state_dict
+        # puts a checkpoint's moments back)
+        engine.exp_avg = engine.exp_avg_sq = None
 
     def _seg_weight_decay(self):
         wd_of = {}

@@ -89,9 +89,10 @@ def test_resnet50_c2_step_parity_vs_fp32_oracle_on_gpu():
     ours = pu.candidate_from(oracle, cfg)
     batch = pu.to_cuda(po.synthetic_batch(b, 224, seed=5, structured=True))
     ref, ref_g = pu.oracle_step_on_gpu(oracle, batch)
+    env = pu.autocast_envelope(oracle, batch)
     got, got_g = pu.candidate_step(ours, batch)
     assert len(got) == 17
-    pu.report_and_check("C2 RN50 B=128 224^2", got, got_g, ref, ref_g)
+    pu.report_and_check("C2 RN50 B=128 224^2", got, got_g, ref, ref_g, envelope=env)
     # run-to-run: bit-identical (same weights, same batch)
     g1 = ours.engine.grads.clone()
     got2, _ = pu.candidate_step(ours, batch)
@@ -155,21 +156,25 @@ def test_resnet50_full_batch_step_properties():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("b,size,warm_b,steps", [(16, 224, 16, 30), (8, 64, 8, 60)])
-def test_resnet152_step_parity_vs_fp32_oracle_on_gpu(b, size, warm_b, steps):
+@pytest.mark.parametrize("b,size", [(16, 224), (8, 64)])
+def test_resnet152_step_parity_vs_fp32_oracle_on_gpu(b, size):
     """ResNet-152 (BASELINE configs 4 / 5: 50 bottleneck blocks, 155 convolutions; the skip-path gradient is
-    accumulated in bf16 by TMA reduce-add 50 times) against the fp32 oracle on the GPU, oracle-warm-started."""
+    accumulated in bf16 by TMA reduce-add 50 times) against the fp32 oracle on the GPU at 224 x 224 (B = 16) and
+    64 x 64 (B = 8), warm-started for 500 Adam steps at B = 8 / 64 x 64 (tests/parity_util.py: why 500)."""
     import parity_util as pu
     from oracle import peclr_oracle as po
 
     cfg = _full_cfg("152", b)
-    oracle = pu.warm_started_oracle(cfg, steps=steps, batch_size=warm_b, size=size)
+    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=500, batch_size=8, size=64)
+    oracle.config = cfg
     ours = pu.candidate_from(oracle, cfg)
     assert len(ours.engine.segs) == 470 and ours.engine.total == 59259456  # SURVEY 8(a)-A11
     batch = pu.to_cuda(po.synthetic_batch(b, size, seed=5, structured=True))
     ref, ref_g = pu.oracle_step_on_gpu(oracle, batch)
+    env = pu.autocast_envelope(oracle, batch)
     got, got_g = pu.candidate_step(ours, batch)
-    pu.report_and_check("RN152 B=%d %d^2" % (b, size), got, got_g, ref, ref_g)
+    tol = (pu.TOL_DLOSS if b >= 16 else pu.TOL_DLOSS_SMALL, pu.TOL_COS_ALL, pu.TOL_COS_TOP)
+    pu.report_and_check("RN152 B=%d %d^2" % (b, size), got, got_g, ref, ref_g, envelope=env, tol=tol)
     g1 = ours.engine.grads.clone()
     got2, _ = pu.candidate_step(ours, batch)
     assert got2["loss"] == got["loss"] and torch.equal(ours.engine.grads, g1)
@@ -179,16 +184,17 @@ def test_resnet152_step_parity_vs_fp32_oracle_on_gpu(b, size, warm_b, steps):
 
 def test_resnet152_c5_accumulation_window():
     """BASELINE config 5's accumulation (accumulate_grad_batches 16) on ResNet-152: 16 micro-batches at scale 1/16
-    through the CUDA-graph path equal the eagerly accumulated gradient bit for bit; one optimiser step at the paper's
-    lr = 1e-4 * sqrt(64 * 16) follows.  (B = 4 per micro-batch at 64 x 64 here; bench.py --model 152 --batch 64
-    --accumulate 16 runs the true size.)"""
+    through the CUDA-graph path equal the eagerly accumulated gradient bit for bit, the accumulated gradient matches
+    the fp32 oracle's, and one optimiser step at the paper's lr = 1e-4 * sqrt(64 * 16) follows.  (B = 8 per micro-batch
+    at 64 x 64 here; bench.py --model 152 --batch 64 --accumulate 16 runs the true size.)"""
     import parity_util as pu
     from oracle import peclr_oracle as po
     from peclr_b200.graphed import GraphedStep
 
-    b, acc = 4, 16
+    b, acc = 8, 16
     cfg = po.default_config(resnet_size="152", batch_size=64, num_samples=64 * 16 * 100, num_of_mini_batch=acc)
-    oracle = pu.warm_started_oracle(cfg, steps=20, batch_size=b, size=64)
+    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=500, batch_size=8, size=64)
+    oracle.config = cfg
     ours = pu.candidate_from(oracle, cfg)
 
     class T:
@@ -221,7 +227,7 @@ def test_resnet152_c5_accumulation_window():
     ref_g = pu.grads_by_group(po.named_grads(oracle))
     got_g = pu.grads_by_group({n: p.grad for n, p in ours.named_parameters() if not n.startswith("encoder.final_layer")})
     cosines = {k: pu.cos(got_g[k], ref_g[k]) for k in ref_g}
-    print("\n[parity C5 window RN152 16 x B=4 64^2] gradient cosines", {k: round(v, 4) for k, v in cosines.items()})
+    print("\n[parity C5 window RN152 16 x B=8 64^2] gradient cosines", {k: round(v, 4) for k, v in cosines.items()})
     assert cosines["all"] >= pu.TOL_COS_ALL and cosines["layer4"] >= pu.TOL_COS_TOP and cosines["head"] >= pu.TOL_COS_TOP
     before = ours.engine.flat.clone()
     for _ in range(2):

@@ -238,3 +238,42 @@ def test_checkpoint_helpers_identical(ref, monkeypatch, tmp_path):
         for f in os.listdir(ckpt_dir):
             os.remove(os.path.join(ckpt_dir, f))
         os.removedirs(ckpt_dir)
+
+
+@pytest.mark.reference
+def test_rn25d_oracle_equals_reference():
+    """The downstream network's oracle restatement (oracle/rn25d_oracle.py) against the reference module itself
+    (src/models/rn_25D_wMLPref.py, imported from /root/reference: it needs only torch + torchvision): same state_dict
+    for the same seed, bit-identical outputs in eval mode, with and without a per-sample camera matrix; and the
+    product's holder module has the same keys and initial values."""
+    import importlib.util
+
+    from oracle.rn25d_oracle import OracleRN25D
+    from peclr_b200.rn_25D_wMLPref import RN_25D_wMLPref
+
+    spec = importlib.util.spec_from_file_location("ref_rn25d", "/root/reference/src/models/rn_25D_wMLPref.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(0)
+    theirs = ref.RN_25D_wMLPref("rn50")
+    torch.manual_seed(0)
+    ours = OracleRN25D("rn50")
+    torch.manual_seed(0)
+    product = RN_25D_wMLPref("rn50")
+    a, b, c = theirs.state_dict(), ours.state_dict(), product.state_dict()
+    assert list(a) == list(b) == list(c) and len(a) == 336
+    assert all(torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]) for k in a)
+    product.load_state_dict(a)  # the released checkpoints' layout loads
+    theirs.eval(), ours.eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    K = torch.tensor([[[400.0, 0.0, 110.0], [0.0, 395.0, 115.0], [0.0, 0.0, 1.0]]]).repeat(2, 1, 1)
+    K[1, 0, 0] = 380.0
+    with torch.no_grad():
+        for kk in (None, K):
+            ra, oa = theirs(x, kk), ours(x, kk)
+            assert set(ra) == set(oa) == {"kp3d", "zrel", "kp2d", "kp25d"}
+            for k in ra:
+                assert torch.equal(ra[k], oa[k]), k
+    with pytest.raises(Exception):
+        RN_25D_wMLPref("rn18")
