@@ -94,13 +94,15 @@ def _group_of(name):
     return {"0": "stem", "1": "stem", "4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}[name.split(".")[2]]
 
 
-def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=60):
+def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=300):
     from oracle import peclr_oracle as po
     from peclr_b200.easydict import EasyDict
     from peclr_b200.hybrid2_model import Hybrid2Model
 
     old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    old_det = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     try:
         cfg = po.default_config(resnet_size="50", batch_size=b, num_samples=b * world * 64)
         torch.manual_seed(0)
@@ -171,6 +173,7 @@ def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=60):
         return res
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = old_det
 
 
 def run_all(engine, b, world, rank, dev):

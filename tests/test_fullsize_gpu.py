@@ -160,12 +160,12 @@ def test_resnet50_full_batch_step_properties():
 def test_resnet152_step_parity_vs_fp32_oracle_on_gpu(b, size):
     """ResNet-152 (BASELINE configs 4 / 5: 50 bottleneck blocks, 155 convolutions; the skip-path gradient is
     accumulated in bf16 by TMA reduce-add 50 times) against the fp32 oracle on the GPU at 224 x 224 (B = 16) and
-    64 x 64 (B = 8), warm-started for 500 Adam steps at B = 8 / 64 x 64 (tests/parity_util.py: why 500)."""
+    64 x 64 (B = 8), warm-started for 1000 Adam steps at B = 8 / 64 x 64 (tests/parity_util.py: why so long)."""
     import parity_util as pu
     from oracle import peclr_oracle as po
 
     cfg = _full_cfg("152", b)
-    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=500, batch_size=8, size=64)
+    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=1000, batch_size=8, size=64)
     oracle.config = cfg
     ours = pu.candidate_from(oracle, cfg)
     assert len(ours.engine.segs) == 470 and ours.engine.total == 59259456  # SURVEY 8(a)-A11
@@ -173,7 +173,7 @@ def test_resnet152_step_parity_vs_fp32_oracle_on_gpu(b, size):
     ref, ref_g = pu.oracle_step_on_gpu(oracle, batch)
     env = pu.autocast_envelope(oracle, batch)
     got, got_g = pu.candidate_step(ours, batch)
-    tol = (pu.TOL_DLOSS if b >= 16 else pu.TOL_DLOSS_SMALL, pu.TOL_COS_ALL, pu.TOL_COS_TOP)
+    tol = (pu.TOL_DLOSS_SMALL, pu.TOL_COS_ALL, pu.TOL_COS_TOP)
     pu.report_and_check("RN152 B=%d %d^2" % (b, size), got, got_g, ref, ref_g, envelope=env, tol=tol)
     g1 = ours.engine.grads.clone()
     got2, _ = pu.candidate_step(ours, batch)
@@ -193,7 +193,7 @@ def test_resnet152_c5_accumulation_window():
 
     b, acc = 8, 16
     cfg = po.default_config(resnet_size="152", batch_size=64, num_samples=64 * 16 * 100, num_of_mini_batch=acc)
-    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=500, batch_size=8, size=64)
+    oracle = pu.warm_started_oracle(_full_cfg("152", 8), steps=1000, batch_size=8, size=64)
     oracle.config = cfg
     ours = pu.candidate_from(oracle, cfg)
 

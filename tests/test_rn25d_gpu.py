@@ -28,6 +28,11 @@ def _oracle(backend, seed=0, settle=6):
 
     torch.manual_seed(seed)
     oracle = OracleRN25D(backend).cuda()
+    with torch.no_grad():
+        # default-initialised fc rows sum 2048 post-ReLU features with random signs: outputs near zero by cancellation,
+        # so their RELATIVE error says nothing.  A positive component makes them keypoint-like magnitudes (tens of
+        # pixels), as trained checkpoints have.
+        oracle.backend_model.fc.weight.add_(0.03)
     oracle.train()
     with torch.no_grad(), pu.strict_fp32():
         for i in range(settle):

