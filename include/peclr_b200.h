@@ -198,6 +198,19 @@ int peclr_weight_transpose(const float* src_flat, void* dst_bf16, const void* ta
 int peclr_stem_pack(const float* w, void* wpack, void* stream);
 int peclr_stem_unpack_grad(const float* gpack, float* g, void* stream);
 
+/* ---- GPU-side two-view augmentation (csrc/augment.cu): the pixel work of SampleAugmenter.transform_sample
+ * (reference src/data_loader/sample_augmenter.py:47-129: rotate = cv2.warpAffine, crop, cv2.resize INTER_AREA, HSV
+ * colour jitter) + ToTensor / Normalize (data_loader/utils.py:287-293), one launch for all N = 2B view images.
+ * src_u8: device buffer of raw 8-bit H x W x 3 images; view_table: N rows of
+ *   { double m[6] (dst->src affine map, inverted as cv2.warpAffine does); int64 src_off (bytes); int32 sh, sw (source
+ *     size); int32 ox, oy, cw, ch (crop box in the rotated image, clipped); double h, s, a, b (HSV factors);
+ *     int32 rotate, jitter (flags) }   -- 120 bytes, peclr_b200/gpu_augment.py VIEW_DTYPE;
+ * out: fp32 [N][3][out_h][out_w] normalised views; stage_u8 (optional, [N][out_h][out_w][3]) the 8-bit image before
+ * ToTensor.  OpenCV's 8-bit arithmetic is reproduced (fixed-point bilinear warp, area resize, integer HSV). */
+int peclr_two_view_augment(const void* src_u8, long long src_bytes, const void* view_table, int n, int out_h,
+                           int out_w, float mean0, float mean1, float mean2, float std0, float std1, float std2,
+                           float* out, void* stage_u8, void* stream);
+
 /* ---- downstream consumer of the exported encoder (csrc/rn25d_head.cu): the head of RN_25D_wMLPref
  * (reference src/models/rn_25D_wMLPref.py:75-134 forward after the backbone, :6-72 ZrootMLP_ref), inference only
  * (eval-mode BatchNorm1d).  out [B][64] = backbone output (fc of the ResNet trunk: peclr_sgemm on the pooled

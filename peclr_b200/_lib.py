@@ -56,6 +56,7 @@ SIGNATURES = {
     "peclr_stem_pack": [P, P, P],
     "peclr_stem_unpack_grad": [P, P, P],
     "peclr_rn25d_head": [P, P, I, I, P, F, F, P, P, P, P, P],
+    "peclr_two_view_augment": [P, L, P, I, I, I, F, F, F, F, F, F, P, P, P],
 }
 _RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong, "peclr_conv2d_wgrad_workspace_bytes": c_longlong,
              "peclr_stem_wgrad_workspace_bytes": c_longlong, "peclr_sgemm_workspace_bytes": c_longlong}

@@ -8,13 +8,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpeclr_b200.so")
 SOURCES = ["abi.cu", "conv_tc.cu", "conv_ops.cu", "bn_act.cu", "head.cu", "ntxent.cu", "equiv_ops.cu", "lars_adam.cu",
-           "rn25d_head.cu"]
+           "rn25d_head.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
 ]
 # --use_fast_math would also flush denormals / relax the fp32 loss chain: those files opt out
-PRECISE = {"ntxent.cu", "equiv_ops.cu", "lars_adam.cu", "head.cu", "bn_act.cu", "rn25d_head.cu"}
+PRECISE = {"ntxent.cu", "equiv_ops.cu", "lars_adam.cu", "head.cu", "bn_act.cu", "rn25d_head.cu", "augment.cu"}
 
 
 def _nvcc():

@@ -145,3 +145,29 @@ def test_ckpt_layout_golden(golden_dir):
     sd = model.state_dict()
     assert list(sd.keys()) == [str(k) for k in gold["rn50_keys"]]
     assert ["x".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in gold["rn50_shapes"]]
+
+
+def test_augmentation_parameters_follow_the_reference_random_stream(golden_dir):
+    """draw_view_params (host side of the GPU augmentation) re-draws, from the stored seed, exactly the parameters the
+    reference's SampleAugmenter drew when the golden file was generated (angle, jitter_x/y, h, s, a, b, crop margin) --
+    same use of Python's `random`, same integer truncations on the 21 joints."""
+    import random
+
+    from peclr_b200.gpu_augment import draw_view_params
+
+    gold = np.load(os.path.join(golden_dir, "augment.npz"))
+    names = ("rotate", "crop", "random_crop", "resize", "color_jitter")
+    for name in (str(c) for c in gold["cases"]):
+        flags = dict(zip(names, (bool(v) for v in gold[name + "_flags"])))
+        rs = tuple(int(v) for v in gold[name + "_resize"])
+        random.seed(int(gold[name + "_seed"]))
+        for v in (1, 2):
+            d = draw_view_params(gold[name + "_joints"], gold[name + "_image"].shape[:2], flags, dict(resize_shape=rs))
+            got = [d["angle"], d["jitter_x"], d["jitter_y"], d["h"], d["s"], d["a"], d["b"], d["crop_margin_scale"]]
+            for g, w in zip(got, gold[f"{name}_v{v}_stored"]):
+                assert (g is None and np.isnan(w)) or float(g) == float(w), (name, v, got)
+            box = gold[f"{name}_v{v}_box"]
+            assert [d["ox"], d["oy"], d["cw"], d["ch"], d["side"]] == [int(x) for x in box], (name, v)
+            if d["angle"] is not None:
+                assert -45 <= d["angle"] <= 45 and float(d["angle"]).is_integer()
+            assert d["jitter_x"] <= 0 or d["ox"] == 0  # = -int(U(0, 15)) unless the box was clipped at the image edge

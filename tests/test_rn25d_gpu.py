@@ -4,7 +4,7 @@ restatement (oracle/rn25d_oracle.py, bit-identical to the reference module -- te
 fp32 on the GPU.
 
 Tolerances: the head kernel alone (fp32, same backbone output on both sides) 1e-5 relative; the whole network with the
-bf16 tensor-core trunk rel-L2 <= 3e-2 on every output (eval-mode BatchNorm; the encoder features measure ~0.7e-2).
+bf16 tensor-core trunk rel-L2 <= 1.5e-2 on every output (eval-mode BatchNorm; measured 0.2e-2 ... 0.7e-2).
 """
 import ctypes
 
@@ -102,7 +102,7 @@ def test_rn25d_inference_vs_fp32_oracle(backend):
         errs = {k: rel_l2(got[k], want[k]) for k in want}
         print("\n[rn25d %s n=%d] rel-L2 vs fp32 oracle" % (backend, n), {k: round(v, 4) for k, v in errs.items()})
         for k in want:
-            assert got[k].shape == want[k].shape and errs[k] < 3e-2, (k, errs[k])
+            assert got[k].shape == want[k].shape and errs[k] < 1.5e-2, (k, errs[k])
     ours.train()
     with pytest.raises(NotImplementedError):
         ours(x)
