@@ -55,6 +55,15 @@ int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, i
 int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
                                 int k, int stride, const void* bn_y, const float* bn_mean, const float* bn_invstd,
                                 const float* bn_gamma, const float* bn_beta, double* scratch, void* stream);
+/* The 1x1 / stride-1 dgrad that COMPLETES the gradient of a residual block's input, i.e. of the previous block's
+ * output out = relu(bn(y) + shortcut) (torchvision Bottleneck.forward, "out += identity; out = self.relu(out)"):
+ * on entry dx holds the part of that gradient gathered so far (shortcut branch, or the down-sampling branch's dgrad),
+ * on exit dx = (dx + dgrad(dy)) * relu'(out) with the ReLU mask taken from the bits peclr_bn_apply wrote
+ * (mask_bits, uint8 [M][Cin/8]), and scratch (double[2*Cin], zeroed by the call) = {sum g, sum g*y} with bn_y = y.
+ * Replaces TMA reduce-add accumulation + peclr_bn_bwd_reduce(mask_mode 3) + the masking inside peclr_bn_bwd_apply
+ * for that block output; follow with peclr_bn_bwd_apply(mask_mode 0) on dx.  Cin multiple of 128. */
+int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                              const void* bn_y, const void* mask_bits, double* scratch, void* stream);
 /* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x).  The pixel dimension is split over thread blocks; the splits'
  * partial products go to `workspace` (peclr_conv2d_wgrad_workspace_bytes for the same geometry; may be NULL when
  * that is 0) and a second kernel adds them to dw in a fixed order. */

@@ -191,6 +191,31 @@ extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int 
                     nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+// 1x1 / stride-1 dgrad that COMPLETES the gradient of a residual block's input (see GemmParams "finish mode"):
+// dx holds the gradient gathered so far (shortcut branch, or the down-sampling branch's dgrad) and receives
+// (dx + dgrad(dy)) * relu'(previous block's output), the mask coming from the bits bn_apply wrote; scratch[0:Cin] =
+// sum g, scratch[Cin:2Cin] = sum g*y for the BatchNorm in front of that ReLU (bn_y = its input).
+extern "C" int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
+                                         int Cout, const void* bn_y, const void* mask_bits, double* scratch,
+                                         void* stream) {
+  if (!dy || !wt || !dx || !bn_y || !mask_bits || !scratch) return PECLR_ERR_ARG;
+  if (Cin % 128 || Cout % 64 || Cin > 2048) return PECLR_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * Cin * sizeof(double), st);
+  if (e != cudaSuccess) return -(int)e;
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  const int64_t M = (int64_t)N * H * W;
+  View4 a = flat_view(dy, M, Cout);
+  View4 d = flat_view(dx, M, Cin);
+  BnReduce br;
+  br.y = bn_y;
+  br.mean = br.invstd = br.gamma = br.beta = nullptr;
+  br.mask_bits = static_cast<const uint8_t*>(mask_bits);
+  br.pix_base = 0, br.pix_w = 1, br.pix_h = 0, br.pix_n = 0;
+  return conv_gemm_launch(&a, 1, wt, Cout, Cin, d, taps, 1, Cout / 64, scratch, scratch + Cin, 0, st, &br);
+}
+
 extern "C" int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
                                            int Cout, int k, int stride, const void* bn_y, const float* bn_mean,
                                            const float* bn_invstd, const float* bn_gamma, const float* bn_beta,

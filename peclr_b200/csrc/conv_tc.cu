@@ -56,7 +56,15 @@ struct GemmParams {
   // g = D * [fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0]; stat_sum += sum g, stat_sumsq += sum g*y
   CUtensorMap y_map;
   const float *bn_mean, *bn_invstd, *bn_gamma, *bn_beta;
-  int bn_reduce;
+  int bn_reduce;  // 0: none; 1: as above; 2: "finish" mode, below
+  // finish mode (the dgrad that COMPLETES the gradient of a residual block's input = the previous block's output):
+  // the tile already in the output tensor (shortcut gradient, or the other branch's dgrad) is loaded through d_map
+  // and added in registers, the sum is masked with that block output's ReLU bits (1 byte per 8 channels, written by
+  // bn_apply) and stored; stat_sum += sum g, stat_sumsq += sum g*y with y = the previous block's last conv output.
+  // One pass instead of TMA reduce-add + a BN-backward reduction pass + a masking pass.
+  const uint8_t* mask_bits;
+  long long pix_base, pix_w, pix_h, pix_n;  // pixel index of view element (w, h, n) = base + w*pix_w + h*pix_h + n*pix_n
+  int mask_row_bytes;
   // filter-row halo mode (HALO kernels): a tap table entry is a GROUP of halo_taps taps that differ only in dh
   // (dh = taps.dh[g] + t).  One (Hb + halo_taps - 1) x Wb input box per group and channel chunk serves all of them:
   // tap t reads the same shared-memory buffer from row t * Wb on (Wb is a multiple of 8, so that offset is a
@@ -85,12 +93,14 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint8_t* sB = sA + n_stages * stage_a;
   uint8_t* sD = sB + n_stages * stage_b;
   uint8_t* sY = sD + (BN / 64) * kStageA;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sY + (p.bn_reduce ? (BN / 64) * kStageA : 0));
+  uint8_t* sG = sY + (p.bn_reduce ? (BN / 64) * kStageA : 0);  // finish mode: the tile already in the output tensor
+  uint64_t* full = reinterpret_cast<uint64_t*>(sG + (p.bn_reduce == 2 ? (BN / 64) * kStageA : 0));
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ybar + 2);
+  uint64_t* gbar = ybar + 2;    // [0] accumulated-gradient tile landed, [1] consumed (finish mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + 2);
   // per-CTA statistics, one private copy per row group ([512/BN][2][cout]): every address has exactly one owner
   // thread, so the per-tile accumulation is a plain read-modify-write in a fixed order (reproducible; shared fp32
   // atomics are CAS loops and would add in arrival order).  When the copies do not fit next to the pipeline stages
@@ -116,6 +126,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8 * CTAS);  // one arrival per epilogue warp (of both CTAs: the leader's barrier)
         mbar_init(&ybar[i], 1);
+        mbar_init(&gbar[i], 1);
       }
       fence_barrier_init();
     }
@@ -189,6 +200,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               phase ^= 1;
             }
           }
+        }
+        if (p.bn_reduce == 2) {  // the gradient tile to add to (needed first, by the TMEM drain)
+          mbar_wait(&gbar[1], (tile_no & 1) ^ 1);
+          mbar_expect_tx(&gbar[0], (BN / 64) * kStageA);
+#pragma unroll
+          for (int bx = 0; bx < BN / 64; ++bx)
+            tma_load_4d(&p.d_map, &gbar[0], sG + bx * kStageA, nt * BN + bx * 64, w0, h0, n0);
         }
         if (p.bn_reduce) {  // this tile's BN input, for the epilogue (own CTA, own barrier)
           mbar_wait(&ybar[1], (tile_no & 1) ^ 1);
@@ -266,8 +284,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
+      const bool finish = p.bn_reduce == 2;
+      if (finish) mbar_wait(&gbar[0], it & 1);
       if (et == 0) tma_wait_group_read0();  // previous tile's TMA store has finished reading sD
       named_bar_sync(1, 256);
+      long long mask_row = -1;  // finish mode: byte offset of this thread's pixel in the ReLU bit mask (-1: off-image)
+      if (finish) {
+        const int wl = row & (p.Wb - 1), hl = (row >> p.log_wb) & (p.Hb - 1), nl = row >> p.log_wbhb;
+        if (w0 + wl < p.d_w && h0 + hl < p.d_h && n0 + nl < p.d_n)
+          mask_row = (p.pix_base + (long long)(w0 + wl) * p.pix_w + (long long)(h0 + hl) * p.pix_h +
+                      (long long)(n0 + nl) * p.pix_n) * p.mask_row_bytes;
+      }
 #pragma unroll
       for (int ci = 0; ci < BN / 64; ++ci) {
         const int chunk = half * (BN / 64) + ci;
@@ -275,6 +302,27 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
         const uint32_t box = sD32 + (chunk >> 1) * kStageA + row * 128;
+        if (finish) {
+          // r += the tile already in the tensor (same swizzled position in sG as the store position in sD), then the
+          // ReLU mask of the block output this is the gradient of: bit k of the word = channel (chunk * 32 + k)
+          const uint32_t gdelta = smem_u32(sG) - sD32;
+          const uint32_t bits = mask_row >= 0
+                                    ? *reinterpret_cast<const uint32_t*>(p.mask_bits + mask_row + ((nt * BN + chunk * 32) >> 3))
+                                    : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c16 = (chunk & 1) * 4 + j;
+            const uint4 g = lds_v4(box + gdelta + ((c16 ^ (row & 7)) << 4));
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = 8 * j + 2 * e;
+              const float v0 = __uint_as_float(r[k]) + bf16_lo(gw[e]), v1 = __uint_as_float(r[k + 1]) + bf16_hi(gw[e]);
+              r[k] = (bits >> k) & 1u ? __float_as_uint(v0) : 0u;
+              r[k + 1] = (bits >> (k + 1)) & 1u ? __float_as_uint(v1) : 0u;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c16 = (chunk & 1) * 4 + j;  // 16-byte chunk inside the 128-byte row
@@ -295,6 +343,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (et == 0) {
+        if (finish) mbar_arrive(&gbar[1]);  // every thread has read its part of sG: the producer may refill it
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
           if (p.reduce_add)
@@ -318,7 +367,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         const uint32_t ydelta = smem_u32(sY) - sD32;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
         float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
-        if (p.bn_reduce) {
+        if (p.bn_reduce == 2) mbar_wait(&ybar[0], it & 1);
+        if (p.bn_reduce == 1) {
           const int ch = nt * BN + col;
           sc0 = p.bn_gamma[ch] * p.bn_invstd[ch];
           sh0 = p.bn_beta[ch] - p.bn_mean[ch] * sc0;
@@ -341,6 +391,19 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               const int wl = r0 & (p.Wb - 1), hl = (r0 >> p.log_wb) & (p.Hb - 1), nl = r0 >> p.log_wbhb;
               if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) v[j] = 0u;
             }
+          }
+          if (p.bn_reduce == 2) {  // the staged values are the masked gradient already
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = lds_u32(base + ydelta + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float a0 = bf16_lo(v[j]), b0 = bf16_hi(v[j]), a1 = bf16_lo(v[j + 1]), b1 = bf16_hi(v[j + 1]);
+              s0 += a0, s1 += b0, s2 += a1, s3 += b1;
+              q0 = fmaf(a0, bf16_lo(u[j]), q0), q1 = fmaf(b0, bf16_hi(u[j]), q1);
+              q2 = fmaf(a1, bf16_lo(u[j + 1]), q2), q3 = fmaf(b1, bf16_hi(u[j + 1]), q3);
+            }
+            continue;
           }
           if (p.bn_reduce) {
             uint32_t u[8];
@@ -718,7 +781,7 @@ template <int BN, int STAGES, int CTAS, bool HALO = false>
 static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
   constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
   // everything but the pipeline stages: alignment slack, output staging (+ y tile), barriers
-  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce ? 2 : 1) + 256;
+  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce == 2 ? 3 : (p.bn_reduce ? 2 : 1)) + 256;
   p.stat_copies = 0;
   if (stats) {
     p.stat_copies = 512 / BN;
@@ -823,6 +886,13 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
     if ((rc = encode_view(&p.y_map, yv, bw, bh, bn))) return rc;
     p.bn_mean = bnr->mean, p.bn_invstd = bnr->invstd, p.bn_gamma = bnr->gamma, p.bn_beta = bnr->beta;
     p.bn_reduce = 1;
+    if (bnr->mask_bits) {
+      if (halo || nout % 128 != 0) return PECLR_ERR_ARG;
+      p.bn_reduce = 2;
+      p.mask_bits = bnr->mask_bits;
+      p.pix_base = bnr->pix_base, p.pix_w = bnr->pix_w, p.pix_h = bnr->pix_h, p.pix_n = bnr->pix_n;
+      p.mask_row_bytes = (int)(nout / 8);
+    }
   }
   const bool pairs = use_cta_pairs() && d_view.w * d_view.h * d_view.n > 128;  // at least two m tiles
   if ((rc = encode_matrix(&p.b_map, w, ktot, nout, pairs ? BN / 2 : BN))) return rc;
@@ -847,6 +917,10 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
     if (BN == 128) return launch_gemm_t<128, 8, 2, true>(p, stats, stream);
     if (BN == 64) return launch_gemm_t<64, 8, 2, true>(p, stats, stream);
     return PECLR_ERR_ARG;
+  }
+  if (p.bn_reduce == 2) {  // three staging tiles (output, y, gradient-so-far): fewer pipeline stages
+    if (pairs) return launch_gemm_t<128, 4, 2>(p, stats, stream);
+    return launch_gemm_t<128, 3, 1>(p, stats, stream);
   }
   if (pairs) {
     if (BN == 256) return launch_gemm_t<256, 4, 2>(p, stats, stream);

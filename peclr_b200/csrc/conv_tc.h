@@ -40,6 +40,11 @@ void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn);
 struct BnReduce {
   const void* y;
   const float *mean, *invstd, *gamma, *beta;
+  // finish mode (mask_bits != nullptr; mean .. beta unused): D = (D_in_tensor + GEMM) masked with the ReLU bits of the
+  // block output D is the gradient of ([pixels][C/8] bytes as bn_apply writes them); sums of g and g*y as above.
+  // Pixel index of view element (w, h, n) = pix_base + w*pix_w + h*pix_h + n*pix_n.
+  const uint8_t* mask_bits = nullptr;
+  long long pix_base = 0, pix_w = 0, pix_h = 0, pix_n = 0;
 };
 
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.

@@ -259,6 +259,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void sts_v4(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");

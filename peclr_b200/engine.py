@@ -44,6 +44,9 @@ class StepEngine:
         self._ws = {}
         self.overlap_wgrad = os.environ.get("PECLR_OVERLAP_WGRAD", "1") != "0"
         self.fuse_bn_reduce = os.environ.get("PECLR_FUSE_BN_REDUCE", "1") != "0"
+        # block-output BatchNorm backward: the dgrad that completes a block input's gradient also masks it with the
+        # previous block's ReLU bits and accumulates that block's BN-backward sums (peclr_conv2d_dgrad_finish)
+        self.fuse_block_bn = os.environ.get("PECLR_FUSE_BLOCK_BN", "1") != "0"
         self._side = None
         # workspaces of the split reductions (ordered, atomics-free: see include/peclr_b200.h).  The conv weight
         # gradients share one (they run in order on one stream), the stem's runs on the main stream and has its own;
@@ -383,8 +386,16 @@ class StepEngine:
             convs = rec["convs"]
             # last conv of the block: BN backward with the block-output ReLU mask; g feeds the shortcut
             conv, bn, x, y, out, sv = convs[-1]
-            dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
-                                    self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
+            if rec.get("prefinished"):
+                # da already is g = (complete gradient) * relu'(out) and scratch holds this BatchNorm's sums: both
+                # came out of the next block's finishing dgrad.  dy goes to its own buffer (g stays the shortcut's).
+                g = da
+                dy = ops.bn_backward(da, None, y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
+                                     self._g(bn, "bias"), scratch=scratch, reduce_done=True)
+                rec["prefinished"] = False
+            else:
+                dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
+                                        self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
             da = None
             wgrad(lambda x=x, dy=dy, conv=conv: ops.conv2d_wgrad(
                 x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"), ws=self._wgrad_ws), x, dy)
@@ -406,18 +417,33 @@ class StepEngine:
                 wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(
                     px, dy, pconv.k, pconv.stride, dw=self._g(pconv, "weight"), ws=self._wgrad_ws), px, dy)
             conv1 = convs[0][0]
+            # the dgrad of conv1 completes the gradient of this block's input = the previous block's output
+            prev = ctx["blocks"][bi - 1] if bi > 0 else None
+            finish = (self.fuse_block_bn and prev is not None and conv1.k == 1 and conv1.stride == 1
+                      and conv1.cin % 128 == 0 and prev["mask"] is not None)
+            if finish:
+                y_prev = prev["convs"][-1][3]
             if "down" in rec:
                 dconv, dbn, yd, dsv = rec["down"]
                 dyd = ops.bn_backward(g, None, yd, dsv, self._p(dbn, "weight"), self._g(dbn, "weight"),
                                       self._g(dbn, "bias"), scratch=scratch, dy=g)
                 wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: ops.conv2d_wgrad(
                     a_in, dyd, 1, dconv.stride, dw=self._g(dconv, "weight"), ws=self._wgrad_ws), a_in, dyd)
-                da = ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride)
-                ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride, out=da, accumulate=True)
+                if finish:  # down-sampling branch first (its stride-2 form only touches a sub-lattice), conv1 finishes
+                    da = ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride)
+                    ops.conv2d_dgrad_finish(dy, self._wt(conv1), da, y_prev, prev["mask"], scratch)
+                else:
+                    da = ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride)
+                    ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride, out=da, accumulate=True)
             else:
-                da = g  # identity shortcut: start from g and add the main branch with a TMA reduce-add
-                ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride, out=da,
-                                 accumulate=True)
+                da = g  # identity shortcut: start from g and add the main branch
+                if finish:
+                    ops.conv2d_dgrad_finish(dy, self._wt(conv1), da, y_prev, prev["mask"], scratch)
+                else:  # (TMA reduce-add)
+                    ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride, out=da,
+                                     accumulate=True)
+            if finish:
+                prev["prefinished"] = True
             if after_stage is not None and (bi == 0 or stage_of[id(self.blocks[bi - 1])] != stage_of[id(blk)]):
                 after_stage(stage_of[id(blk)])
         # stem: max-pool + ReLU + BN backward, then the 7x7 weight gradient

@@ -103,6 +103,19 @@ def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta,
     return dx
 
 
+def conv2d_dgrad_finish(dy, wt, dx, bn_y, mask_bits, scratch):
+    """1x1 / stride-1 dgrad completing a residual block's input gradient IN PLACE: dx <- (dx + dgrad(dy)) masked with
+    the previous block output's ReLU bits; scratch (fp64 [2*Cin]) <- sum g, sum g*y for that block's last BatchNorm
+    (bn_y = its input).  Follow with bn_backward(dx, None, bn_y, ..., reduce_done=True)."""
+    _need_cuda(dy, wt, dx, bn_y, mask_bits)
+    n, h, wd, cin = dx.shape
+    cout = dy.shape[-1]
+    assert scratch.dtype == f64 and scratch.numel() >= 2 * cin and mask_bits.dtype == torch.uint8
+    assert tuple(bn_y.shape) == tuple(dx.shape) and mask_bits.numel() == n * h * wd * cin // 8
+    _lib.call("peclr_conv2d_dgrad_finish", dy, wt, dx, n, h, wd, cin, cout, bn_y, mask_bits, scratch, _s())
+    return dx
+
+
 def conv2d_wgrad(x, dy, k, stride, dw=None, ws=None):
     """dw [Cout,k*k,Cin] fp32 += dy^T im2col(x).  ws: the Workspace the pixel splits' partials go through."""
     _need_cuda(x, dy)

@@ -496,3 +496,40 @@ def test_split_reductions_are_reproducible(ops):
     torch.cuda.synchronize()
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", [(2, 56, 56, 256, 64), (3, 28, 28, 512, 128), (4, 14, 14, 1024, 256),
+                                  (4, 7, 7, 2048, 512), (1, 8, 8, 256, 64), (5, 5, 5, 128, 64)])
+def test_dgrad_finish(ops, case):
+    """The finishing dgrad: dx <- (dx + dgrad(dy)) * relu'(previous block output) from the bit mask, plus that block's
+    BN-backward sums, against the same thing composed from fp32 torch operations."""
+    n, h, w, cin, cout = case  # the conv maps cin -> cout; its dgrad produces cin channels
+    g = torch.Generator(device="cuda").manual_seed(31)
+    wt = (torch.randn(cout, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    dy = nhwc(torch.randn(n, cout, h, w, device="cuda", generator=g).bfloat16())
+    acc = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()  # gradient gathered so far
+    y_prev = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    keep = torch.rand(n, h, w, cin, device="cuda", generator=g) > 0.4  # ReLU mask of the previous block's output
+    bits = (keep.view(-1, cin // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(
+        -1, dtype=torch.uint8).contiguous()
+    wt_t = krsc(wt).permute(2, 1, 0).contiguous()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float(), dy.permute(0, 3, 1, 2).float())
+    want = (acc.float() + nhwc(ref)) * keep
+    dx = acc.clone()
+    scratch = torch.full((2 * cin,), 7.0, device="cuda", dtype=torch.float64)
+    ops.conv2d_dgrad_finish(dy, wt_t, dx, y_prev, bits, scratch)
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float(), want) < 1e-2, rel_l2(dx.float(), want)
+    assert float(dx.float()[~keep].abs().max()) == 0  # masked positions are exact zeros
+    gm = dx.double().reshape(-1, cin)
+    sums = torch.cat([gm.sum(0), (gm * y_prev.double().reshape(-1, cin)).sum(0)])
+    assert (scratch - sums).abs().max().item() <= 1e-5 * sums.abs().max().item()
+    # reproducible, and consistent with the unfused sequence (reduce-add dgrad, then mask) up to one bf16 rounding
+    dx2 = acc.clone()
+    scratch2 = torch.empty_like(scratch)
+    ops.conv2d_dgrad_finish(dy, wt_t, dx2, y_prev, bits, scratch2)
+    old = acc.clone()
+    ops.conv2d_dgrad(dy, wt_t, (n, h, w, cin), 1, 1, out=old, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx) and torch.equal(scratch2, scratch)
+    assert rel_l2(dx.float(), old.float() * keep) < 6e-3
