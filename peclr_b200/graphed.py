@@ -10,10 +10,18 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, model, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0, warmup: int = 2):
+    def __init__(self, model, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0, warmup: int = 2,
+                 share_inputs: bool = False):
+        """share_inputs: use the example batch's own (device) tensors as the captured input buffers instead of
+        clones -- a producer that writes the next batch straight into them (e.g. the GPU augmentation's `out=`)
+        then needs no copy per step."""
         dev = model.engine.device
         self.model = model
-        self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        if share_inputs:
+            assert all(v.device == dev for v in example_batch.values() if torch.is_tensor(v))
+            self.static = {k: v for k, v in example_batch.items() if torch.is_tensor(v)}
+        else:
+            self.static = {k: v.to(dev).clone() for k, v in example_batch.items() if torch.is_tensor(v)}
         self.grad_scale = grad_scale
         self.graph = torch.cuda.CUDAGraph()
         model.train()
@@ -57,6 +65,8 @@ class GraphedStep:
         from . import _lib
 
         for k, dst in self.static.items():
+            if k not in batch:
+                continue  # (extra keys of the example batch the model does not read)
             src = batch[k]
             if src.shape != dst.shape:
                 raise ValueError(f"GraphedStep was captured for {k} of shape {tuple(dst.shape)}, got {tuple(src.shape)}")

@@ -316,3 +316,37 @@ def test_model_checkpoint_restores_top_k_bookkeeping(tmp_path):
     cb2 = ModelCheckpoint(save_top_k=2, dirpath=str(d))
     cb2.restore_state({}, str(d / "epoch=3.ckpt"))  # a checkpoint without the record (e.g. the reference's)
     assert [p for _, p in cb2.best] == [str(d / "epoch=0.ckpt"), str(d / "epoch=3.ckpt")]
+
+
+def test_batched_augmentation_parameters_equal_the_scalar_specification():
+    """draw_batch_params (vectorised, what GpuTwoViewAugmenter uses per step) == draw_view_params (the scalar
+    restatement of SampleAugmenter's parameter drawing, pinned to the reference by the golden file): same random stream,
+    same integers, bit-identical inverted warp matrices."""
+    import random
+
+    from peclr_b200.gpu_augment import GpuTwoViewAugmenter, draw_batch_params, draw_view_params, invert_affine
+
+    rs = np.random.RandomState(0)
+    b = 96
+    joints = (rs.randn(b, 21, 3) * rs.uniform(5, 45, (b, 1, 1)) + rs.uniform(30, 200, (b, 1, 3))).astype(np.float32)
+    for flags in (dict(rotate=True, crop=True, random_crop=True, resize=True, color_jitter=True),
+                  dict(rotate=False, crop=True, random_crop=False, resize=True, color_jitter=False),
+                  dict(rotate=True, crop=False, random_crop=True, resize=True, color_jitter=True)):
+        random.seed(3)
+        scalar = [(draw_view_params(x, (224, 240), flags), draw_view_params(x, (224, 240), flags)) for x in joints]
+        random.seed(3)
+        bp = draw_batch_params(joints, (224, 240), flags)
+        for i in range(b):
+            for v in (0, 1):
+                d = scalar[i][v]
+                for k in ("ox", "oy", "cw", "ch", "side", "jitter_x", "jitter_y", "crop_margin_scale"):
+                    assert d[k] == bp[k][v, i], (k, i, v)
+                if flags["rotate"]:
+                    assert d["angle"] == bp["angle"][v, i]
+                    assert np.array_equal(invert_affine(d["m_fwd"]), bp["m_inv"][v, i])
+                if flags["color_jitter"]:
+                    assert [d["h"], d["s"], d["a"], d["b"]] == list(bp["hsab"][v, i])
+        aug = GpuTwoViewAugmenter(flags, device="cpu")
+        assert np.array_equal(aug.table(scalar, b, 224, 240), aug.batch_table(bp, b, 224, 240))
+    with pytest.raises(NotImplementedError):
+        GpuTwoViewAugmenter(dict(resize=True, gaussian_blur=True))
