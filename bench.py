@@ -166,12 +166,20 @@ def measure(ctx, model_size, batch, size, accumulate, steps, warmup, sample_cloc
         """One optimiser step = `accumulate` micro-steps (training_step + backward; with the CUDA graph replayed
         from the capture: same kernels, one submission each), then gradient exchange + the fused optimiser."""
         opt.zero_grad()
+        synced = False
         for j in range(accumulate):
             mb = get_batch(j)
-            loss = graphed(mb)["loss"] if graphed is not None else eager_micro(mb)
+            closing = j == accumulate - 1  # (data parallel: this micro-step all-reduces its gradients as it goes)
+            model.enable_overlapped_sync(closing)
+            if graphed is not None:
+                loss = graphed(mb, sync=closing)["loss"]
+                synced = graphed.synced
+            else:
+                loss = eager_micro(mb)
             if after_micro is not None:
                 after_micro(j, loss)
-        model.sync_gradients()
+        if not synced:
+            model.sync_gradients()
         opt.step()
         sched.step()
         return loss
@@ -370,17 +378,22 @@ def e2e_from_raw_images(ctx, model, opt, sched, batch, size, accumulate, steps, 
         i = 0
         for _ in range(n):
             opt.zero_grad()
-            for _ in range(accumulate):
+            synced = False
+            for j in range(accumulate):
                 mb = aug(raw[i % n_host], joints[i % n_host], out=views, copy_stream=copy_stream)
+                closing = j == accumulate - 1
+                model.enable_overlapped_sync(closing)
                 if graphed is not None:
-                    loss = graphed(mb)["loss"]
+                    loss = graphed(mb, sync=closing)["loss"]
+                    synced = graphed.synced
                 else:
                     out = model.training_step(mb, 0)
                     (out["loss"] * scale).backward()
                     loss = out["loss"]
                 loss_host.copy_(loss.detach(), non_blocking=True)
                 i += 1
-            model.sync_gradients()
+            if not synced:
+                model.sync_gradients()
             opt.step()
             sched.step()
         torch.cuda.current_stream().synchronize()

@@ -54,11 +54,70 @@ class BaseModel(LightningModule):
         self.engine.zero_grad()
         self.engine.attach_grads()
 
-    def sync_gradients(self):
-        """Data-parallel gradient exchange (sum over ranks; see peclr_b200.lightning)."""
+    # ---- data-parallel gradient exchange (SUM over ranks: the fused loss already returns the gradient of the
+    # GLOBAL-batch mean w.r.t. the local rows) -------------------------------------------------------
+    # Overlapped with backward: the flat gradient buffer is in named_parameters() order, so the ResNet stages are four
+    # contiguous ranges [stem + layer1 | layer2 | layer3 | layer4 + head].  backward_trunk reports a stage as soon as
+    # its gradients are final (layer4 first); its range is all-reduced right then on a communication stream, next to
+    # the rest of the backward pass.  Inside a CUDA-graph capture the collectives are captured with the step.
+    @staticmethod
+    def _dp_world():
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _stage_ranges(self):
+        eng = self.engine
+        if getattr(self, "_ranges_for", None) is not eng.segs:
+            first = {}
+            for s in eng.segs:
+                key = s.name.split(".")[2] if s.name.startswith("encoder.features.") else "head"
+                first.setdefault(key, s.begin)
+            l2, l3, l4 = first["5"], first["6"], first["7"]
+            # reported stage -> range to reduce: 3 = layer4 (+ head, final since backward_head), 2 = layer3,
+            # 1 = layer2, -1 = end of backward (layer1 + stem)
+            self._ranges = {3: (l4, eng.total), 2: (l3, l4), 1: (l2, l3), -1: (0, l2)}
+            self._ranges_for = eng.segs
+        return self._ranges
+
+    def enable_overlapped_sync(self, on: bool = True):
+        """Arms the per-stage all-reduce for the backward passes that follow (the Trainer / bench arm it for the micro-step
+        that closes an accumulation window).  No-op on one GPU."""
+        if on and self._dp_world() > 1:
+            self._after_stage_hook = self._reduce_stage
+        else:
+            self._after_stage_hook = None
+
+    def _reduce_stage(self, stage):
+        import torch.distributed as dist
+
+        rng = self._stage_ranges().get(stage)
+        if rng is None:
+            return
+        eng = self.engine
+        if getattr(self, "_comm", None) is None or self._comm.device != eng.device:
+            self._comm = torch.cuda.Stream(device=eng.device)
+        cur = torch.cuda.current_stream()
+        self._comm.wait_stream(cur)
+        if eng.overlap_wgrad and eng._side is not None:
+            self._comm.wait_stream(eng._side)  # the stage's weight gradients run on the engine's side stream
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(eng.grads[rng[0]:rng[1]], op=dist.ReduceOp.SUM)
+        self._pending_sync = True
+        if stage == -1:
+            cur.wait_stream(self._comm)  # end of backward: join (inside a capture this closes the forked stream)
+
+    def sync_gradients(self):
+        """Completes the data-parallel gradient exchange of this optimiser step: waits for the per-stage reductions
+        if the backward pass issued them, else reduces the whole flat buffer in one call."""
+        import torch.distributed as dist
+
+        if self._dp_world() <= 1:
+            return
+        if getattr(self, "_pending_sync", False):
+            torch.cuda.current_stream().wait_stream(self._comm)
+            self._pending_sync = False
+        else:
             dist.all_reduce(self.engine.grads, op=dist.ReduceOp.SUM)
 
     # ---- reference API -----------------------------------------------------------------------------------

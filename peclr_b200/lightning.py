@@ -252,6 +252,14 @@ class Trainer:
             t0, seen = time.time(), 0
             for batch_idx, batch, is_last in self._with_last_flag(train_dataloader, self.limit_train_batches):
                 batch = self._to_device(batch, device)
+                # Lightning 1.0.8 steps when the accumulation window is full AND on the final batch of the epoch (a
+                # partial window: the loss keeps its 1 / accumulate_grad_batches scale), so no gradient leaks into
+                # the next epoch's first window
+                closing = (batch_idx + 1) % acc == 0 or is_last
+                synced = False
+                # data parallel: the micro-step that closes the window all-reduces its gradients stage by stage
+                # while its backward pass is still running
+                model.enable_overlapped_sync(closing)
                 if self.use_cuda_graph:
                     # same work as the eager branch below, submitted as one captured CUDA graph
                     if graphed is None:
@@ -260,7 +268,8 @@ class Trainer:
                         graphed = GraphedStep(model, batch, grad_scale=1.0 / acc)
                         opt.zero_grad()
                     if graphed.matches(batch):
-                        out = graphed(batch)
+                        out = graphed(batch, sync=closing)
+                        synced = graphed.synced
                         outputs.append({k: v.clone() for k, v in out.items()})
                     else:  # e.g. a short last batch: same kernels, submitted eagerly
                         out = model.forward_backward(batch, 1.0 / acc)
@@ -271,11 +280,9 @@ class Trainer:
                     (out["loss"] / acc).backward()
                     outputs.append({k: v.detach() for k, v in out.items()})
                 seen += 2 * batch["transformed_image1"].shape[0] * self.world_size
-                # Lightning 1.0.8 steps when the accumulation window is full AND on the final batch of the epoch (a
-                # partial window: the loss keeps its 1 / accumulate_grad_batches scale), so no gradient leaks into
-                # the next epoch's first window
-                if (batch_idx + 1) % acc == 0 or is_last:
-                    model.sync_gradients()
+                if closing:
+                    if not synced:
+                        model.sync_gradients()
                     opt.step()
                     opt.zero_grad()
                     sched.step()

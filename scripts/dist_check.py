@@ -132,6 +132,18 @@ def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=300):
         ours.sync_gradients()
         torch.cuda.synchronize()
         res = {"pass": True}
+        # the same step with the gradient all-reduce overlapped with backward (one collective per ResNet stage on a
+        # communication stream) must give the monolithic all-reduce's gradients
+        mono = ours.engine.grads.clone()
+        ours.zero_grad()
+        ours.enable_overlapped_sync(True)
+        ours.training_step(shards[rank], 0)["loss"].backward()
+        ours.sync_gradients()
+        ours.enable_overlapped_sync(False)
+        torch.cuda.synchronize()
+        ov = float((ours.engine.grads - mono).abs().max() / mono.abs().max())
+        res["overlapped_allreduce_rel_diff"] = _max_over_ranks(ov, dev)
+        res["pass"] = res["overlapped_allreduce_rel_diff"] <= 1e-6
         if rank == 0:
             # SURVEY 8(e) oracle: R shards through the same weights (BN statistics per shard), global-batch NT-Xent
             # (the running statistics move from shard to shard; the training-mode forward does not read them)
@@ -158,8 +170,9 @@ def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=300):
             dloss = abs(float(out["loss"]) - float(loss))
             ok = dloss <= TOL_DLOSS and cosines["all"] >= TOL_COS_ALL and cosines["layer4"] >= TOL_COS_TOP and \
                 cosines["head"] >= TOL_COS_TOP
-            res = {"dp_loss_ours": float(out["loss"]), "dp_loss_oracle": float(loss), "dp_dloss": dloss,
-                   "dp_grad_cos": {k: round(v, 4) for k, v in cosines.items()}, "pass": bool(ok)}
+            res.update({"dp_loss_ours": float(out["loss"]), "dp_loss_oracle": float(loss), "dp_dloss": dloss,
+                        "dp_grad_cos": {k: round(v, 4) for k, v in cosines.items()},
+                        "pass": bool(ok and res["pass"])})
         # the summed gradient must be the same on every rank after the all-reduce
         g = ours.engine.grads
         g0 = g.clone()
