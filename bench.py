@@ -328,7 +328,7 @@ def measure(ctx, model_size, batch, size, accumulate, steps, warmup, sample_cloc
            "gpu_launches": int(launches), "roofline": roof, "final_loss": final_loss,
            "clocks": sampler.summary() if sampler is not None else None, "micro_bytes": micro_bytes,
            "kernels_per_micro_step": graphed.kernels_per_replay if graphed is not None else None}
-    del graphed, model, opt, sched, staged, resident, host
+    del graphed, model, opt, sched, resident, host
     torch.cuda.empty_cache()
     return res
 
