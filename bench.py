@@ -357,30 +357,36 @@ def e2e_from_raw_images(ctx, model, opt, sched, batch, size, accumulate, steps, 
            for _ in range(n_host)]
     rs = np.random.RandomState(60 + rank)
     joints = [(rs.randn(batch, 21, 3) * size * 0.12 + size * 0.5).astype(np.float32) for _ in range(n_host)]
-    views = torch.empty((2 * batch, 3, size, size), dtype=torch.float32, device=dev)
-    example = aug(raw[0], joints[0], out=views)
+    example = aug(raw[0], joints[0])
     torch.cuda.synchronize()
     scale = 1.0 / accumulate
     graphed = None
     if not no_graph:
         from peclr_b200.graphed import GraphedStep
 
-        # the captured step reads its images straight from `views`, which the augmentation kernel fills: no copy
-        # (only the images are shared: the small per-sample tensors live in the augmenter's upload slots, which the
-        # copy stream refills while a step may still read the captured inputs -> private clones for those)
-        shared = {k: (v if k.startswith("transformed_image") else v.clone()) for k, v in example.items()}
-        graphed = GraphedStep(model, shared, grad_scale=scale, share_inputs=True)
+        graphed = GraphedStep(model, example, grad_scale=scale)
     copy_stream = torch.cuda.Stream()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     small_bytes = aug._staging["slots"][0]["host"].numel()
 
+    def prepare(i):
+        """Upload + augmentation of micro-batch i on the copy stream (overlaps the compute of micro-batch i - 1)."""
+        mb = aug(raw[i % n_host], joints[i % n_host], copy_stream=copy_stream, kernel_on_copy_stream=True)
+        return mb, aug.last_ready
+
     def run(n):
+        total = n * accumulate
+        cur = torch.cuda.current_stream()
+        nxt = prepare(0)
         i = 0
         for _ in range(n):
             opt.zero_grad()
             synced = False
             for j in range(accumulate):
-                mb = aug(raw[i % n_host], joints[i % n_host], out=views, copy_stream=copy_stream)
+                mb, ready = nxt
+                if i + 1 < total:
+                    nxt = prepare(i + 1)
+                cur.wait_event(ready)
                 closing = j == accumulate - 1
                 model.enable_overlapped_sync(closing)
                 if graphed is not None:
@@ -396,7 +402,7 @@ def e2e_from_raw_images(ctx, model, opt, sched, batch, size, accumulate, steps, 
                 model.sync_gradients()
             opt.step()
             sched.step()
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
 
     run(3 if accumulate == 1 else 1)
     barrier()

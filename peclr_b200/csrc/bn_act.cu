@@ -120,6 +120,8 @@ __device__ __forceinline__ void bn_bookkeeping(const float (&mean)[8], const flo
 
 template <int kRows>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = a.C >> 3;  // threads per row
   const int rows_per_block = 256 / tpr;
   const int cg = threadIdx.x % tpr;
@@ -217,6 +219,8 @@ struct BnBwdArgs {
 template <bool kApply, int kMask, int kRows>
 __global__ void __launch_bounds__(256, kApply ? 2 : 3) bn_bwd_kernel(const BnBwdArgs a) {
   __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][kApply ? 1 : 9];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = a.C >> 3;
   const int rows_per_block = 256 / tpr;
   const int cg = threadIdx.x % tpr;
@@ -333,10 +337,10 @@ static int elt_rows() {
 template <bool kApply, int kRows>
 static void launch_bn_bwd_r(const BnBwdArgs& a, int grid, cudaStream_t st) {
   switch (a.mask_mode) {
-    case 0: bn_bwd_kernel<kApply, 0, kRows><<<grid, 256, 0, st>>>(a); break;
-    case 1: bn_bwd_kernel<kApply, 1, kRows><<<grid, 256, 0, st>>>(a); break;
-    case 2: bn_bwd_kernel<kApply, 2, kRows><<<grid, 256, 0, st>>>(a); break;
-    default: bn_bwd_kernel<kApply, 3, kRows><<<grid, 256, 0, st>>>(a); break;
+    case 0: launch_pdl(bn_bwd_kernel<kApply, 0, kRows>, grid, 256, 0, st, a); break;
+    case 1: launch_pdl(bn_bwd_kernel<kApply, 1, kRows>, grid, 256, 0, st, a); break;
+    case 2: launch_pdl(bn_bwd_kernel<kApply, 2, kRows>, grid, 256, 0, st, a); break;
+    default: launch_pdl(bn_bwd_kernel<kApply, 3, kRows>, grid, 256, 0, st, a); break;
   }
 }
 template <bool kApply>
@@ -372,6 +376,8 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
                                                                 float* invstd_out, float* running_mean,
                                                                 float* running_var, int N, int H, int W, float eps,
                                                                 float momentum) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = 64, tpr = 8;
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
@@ -478,6 +484,8 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
                                                             __nv_bfloat16* __restrict__ g_out, double* scratch, int N,
                                                             int H, int W) {
   __shared__ float red[2][256][9];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = 64, tpr = 8;
   const int cg = threadIdx.x % tpr, roff = threadIdx.x / tpr;
   const int c0 = cg * 8;
@@ -557,6 +565,8 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
 // ---- global average pool: x [N][HW][C] bf16 -> out [N][C] fp32 ; and its backward -------------------
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* out, int N,
                                                           int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = C >> 3;
   const long long total = (long long)N * tpr;
   const float inv = 1.f / (float)HW;
@@ -581,6 +591,8 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* _
 
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* dx, int N,
                                                           int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = C >> 3;
   const long long total = (long long)N * HW * tpr;
   const float inv = 1.f / (float)HW;
@@ -603,6 +615,8 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                          __nv_bfloat16* __restrict__ out, int B1, int Ntot, int H,
                                                          int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Hs = H / 2 + 3, Ws = W / 2 + 4;
   const size_t cs = (size_t)H * W;
   // one block iteration = one padded row (n, yp); threads walk the padded blocks (coalesced float2 plane reads)
@@ -689,8 +703,8 @@ extern "C" int peclr_bn_apply(const void* y, const double* sum, const double* su
   const int rows_per_block = 256 / (C / 8);
   const int kr = elt_rows();
   const int grid = grid_for(M, rows_per_block * kr);
-  if (kr == 2) bn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  else bn_apply_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  if (kr == 2) launch_pdl(bn_apply_kernel<2>, grid, 256, 0, (cudaStream_t)stream, a);
+  else launch_pdl(bn_apply_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
   return last_error();
 }
 
@@ -724,9 +738,9 @@ extern "C" int peclr_stem_bn_relu_pool(const void* y, const double* sum, const d
                                        float* invstd_out, float* running_mean, float* running_var, int N, int H,
                                        int W, float eps, float momentum, void* stream) {
   if ((H & 1) || (W & 1)) return -1001;
-  stem_bn_relu_pool_kernel<<<grid_for((long long)N * (H / 2), 1, 4), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, (uint8_t*)idx_out, mean_out, invstd_out, running_mean,
-      running_var, N, H, W, eps, momentum);
+  launch_pdl(stem_bn_relu_pool_kernel, grid_for((long long)N * (H / 2), 1, 4), 256, 0, (cudaStream_t)stream,
+             (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, (uint8_t*)idx_out, mean_out, invstd_out, running_mean,
+             running_var, N, H, W, eps, momentum);
   return last_error();
 }
 
@@ -736,30 +750,30 @@ extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const voi
   if ((H & 1) || (W & 1) || !idx) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * 64 * sizeof(double), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
-  stem_pool_bwd_kernel<<<grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch, N, H,
-      W);
+  launch_pdl(stem_pool_bwd_kernel, grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream,
+             (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch,
+             N, H, W);
   return last_error();
 }
 
 extern "C" int peclr_avgpool_fwd(const void* x, float* out, int N, int HW, int C, void* stream) {
   if (C % 8) return -1001;
-  avgpool_fwd_kernel<<<grid_for((long long)N * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, N,
-                                                                                              HW, C);
+  launch_pdl(avgpool_fwd_kernel, grid_for((long long)N * (C / 8), 256), 256, 0, (cudaStream_t)stream, (const bf16*)x,
+             out, N, HW, C);
   return last_error();
 }
 
 extern "C" int peclr_avgpool_bwd(const float* dout, void* dx, int N, int HW, int C, void* stream) {
   if (C % 8) return -1001;
-  avgpool_bwd_kernel<<<grid_for((long long)N * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(dout, (bf16*)dx, N,
-                                                                                                   HW, C);
+  launch_pdl(avgpool_bwd_kernel, grid_for((long long)N * HW * (C / 8), 256), 256, 0, (cudaStream_t)stream, dout,
+             (bf16*)dx, N, HW, C);
   return last_error();
 }
 
 extern "C" int peclr_stem_input(const float* x1, const float* x2, void* out, int B, int H, int W, void* stream) {
   if ((H & 1) || (W & 1) || B < 1 || !x1) return -1001;
   const int ntot = x2 ? 2 * B : B;  // x2 == NULL: a plain batch of B images (inference / odd batch sizes)
-  stem_input_kernel<<<grid_for((long long)ntot * (H / 2 + 3), 1, 8), 256, 0, (cudaStream_t)stream>>>(
-      x1, x2, (bf16*)out, B, ntot, H, W);
+  launch_pdl(stem_input_kernel, grid_for((long long)ntot * (H / 2 + 3), 1, 8), 256, 0, (cudaStream_t)stream, x1, x2,
+             (bf16*)out, B, ntot, H, W);
   return last_error();
 }

@@ -137,11 +137,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   if (want_stats && warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.stat_copies * 2 * p.cout; i += 256) sStat[i] = 0.f;
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   // work items: (pair of) m tiles x n tile; CTA `cta_rank` of a pair owns m tile 2 * pair + cta_rank
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -814,15 +816,26 @@ static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, p);
   return e == cudaSuccess ? 0 : -(int)e;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
 }
 
 static bool use_cta_pairs() {

@@ -35,6 +35,23 @@ struct TapTable {
 
 void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn);
 
+// Programmatic dependent launch for the kernels of the main stream's dependency chain (ptx.cuh: pdl_wait).
+// PECLR_PDL=0 launches them with plain stream serialization (A/B switch).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Fused BatchNorm-backward reduction in the epilogue: y = input of the BatchNorm (+ReLU) whose output gradient this
 // GEMM produces (same geometry as D); stat_sum / stat_sumsq then receive sum g and sum g*y per channel.
 struct BnReduce {

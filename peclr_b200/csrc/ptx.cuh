@@ -259,6 +259,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
   return v;
 }
+// Programmatic dependent launch (the kernels of a step form one dependency chain per stream): a kernel launched with
+// the programmatic-stream-serialization attribute may become resident and run its prologue (barrier / TMEM setup,
+// descriptor prefetch, index arithmetic) while its predecessor is still running; pdl_wait() blocks until the
+// predecessor has completed and its memory is visible -- it must precede the first global-memory access.
+// pdl_launch_dependents() lets the successor start that early.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n"); }
+
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
