@@ -997,7 +997,10 @@ static int wgrad_plan(const View4& dy_view, int num_taps, int cin, int cout, Wgr
     split_waves = e ? atoi(e) : 1;
     if (split_waves < 1) split_waves = 1;
   }
-  int ksplit = (split_waves * sm_count() + base_units - 1) / base_units;
+  // as many pixel splits as keep the WHOLE grid resident at once (one CTA per SM: 200 KB of shared memory, all of
+  // TMEM): rounding up instead put e.g. 160 or 192 CTAs on 148 SMs, a second wave that ran on a handful of SMs and
+  // doubled the kernel's duration (profiles/conv_wgrad_r02_ncu_full.txt: SMs active 50 % of the elapsed time)
+  int ksplit = (split_waves * sm_count()) / base_units;
   const int max_split = (chunks + 7) / 8;  // at least 8 pixel chunks (512 pixels) per unit
   if (ksplit > max_split) ksplit = max_split;
   if (ksplit < 1) ksplit = 1;
