@@ -36,18 +36,38 @@ struct Px {
   int c[3];
 };
 
-// value of the ROTATED image at integer (xr, yr): cv2.warpAffine, bit for bit
-__device__ __forceinline__ Px rotated_pixel(const uint8_t* __restrict__ img, const AugView& v, int xr, int yr) {
+// Fixed-point source coordinates of cv2.warpAffine: X = (X0(yr) + adelta(xr)) >> 5 with X0 = rn((m1*yr + m2)*1024) + 16,
+// adelta = rn(m0*xr*1024) (and Y likewise).  The column terms of a block's crop columns are computed once per block
+// into shared memory and the row terms once per thread and row: the inner loops are integer-only (fp64 is slow here).
+struct RowTerm {
+  int X0, Y0;
+};
+__device__ __forceinline__ RowTerm row_term(const AugView& v, int yr) {
+  RowTerm t;
+  t.X0 = __double2int_rn((v.m[1] * yr + v.m[2]) * 1024.0) + 16;
+  t.Y0 = __double2int_rn((v.m[4] * yr + v.m[5]) * 1024.0) + 16;
+  return t;
+}
+
+// value of the ROTATED image at integer (xr, yr): cv2.warpAffine, bit for bit.  cols = {adelta, bdelta} of the crop's
+// columns (index xr - ox) in shared memory, or nullptr (computed here).
+__device__ __forceinline__ Px rotated_pixel(const uint8_t* __restrict__ img, const AugView& v, int xr, int yr,
+                                            const RowTerm& rt, const int2* cols) {
   Px o;
   if (!v.rotate) {
     const uint8_t* p = img + ((size_t)yr * v.sw + xr) * 3;
     o.c[0] = p[0], o.c[1] = p[1], o.c[2] = p[2];
     return o;
   }
-  const int X0 = __double2int_rn((v.m[1] * yr + v.m[2]) * 1024.0) + 16;
-  const int Y0 = __double2int_rn((v.m[4] * yr + v.m[5]) * 1024.0) + 16;
-  const int X = (X0 + __double2int_rn(v.m[0] * xr * 1024.0)) >> 5;
-  const int Y = (Y0 + __double2int_rn(v.m[3] * xr * 1024.0)) >> 5;
+  int ad, bd;
+  if (cols) {
+    const int2 c = cols[xr - v.ox];
+    ad = c.x, bd = c.y;
+  } else {
+    ad = __double2int_rn(v.m[0] * xr * 1024.0), bd = __double2int_rn(v.m[3] * xr * 1024.0);
+  }
+  const int X = (rt.X0 + ad) >> 5;
+  const int Y = (rt.Y0 + bd) >> 5;
   const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
   const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
   const bool x0 = sx >= 0 && sx < v.sw, x1 = sx + 1 >= 0 && sx + 1 < v.sw;
@@ -150,10 +170,18 @@ __global__ void __launch_bounds__(128) two_view_augment_kernel(const uint8_t* __
                                                                const AugView* __restrict__ views, int n, int dh, int dw,
                                                                float m0, float m1, float m2, float s0, float s1,
                                                                float s2, float* __restrict__ out,
-                                                               uint8_t* __restrict__ stage) {
+                                                               uint8_t* __restrict__ stage, int cols_cap) {
+  extern __shared__ int2 s_cols[];
   const int img_i = blockIdx.y, dy = blockIdx.x;
   const AugView v = views[img_i];
   const uint8_t* img = src + v.src_off;
+  const int2* cols = nullptr;
+  if (v.rotate && v.cw <= cols_cap) {
+    for (int i = threadIdx.x; i < v.cw; i += blockDim.x)
+      s_cols[i] = make_int2(__double2int_rn(v.m[0] * (v.ox + i) * 1024.0), __double2int_rn(v.m[3] * (v.ox + i) * 1024.0));
+    cols = s_cols;
+  }
+  __syncthreads();
   for (int dx = threadIdx.x; dx < dw; dx += blockDim.x) {
     Px px;
     px.c[0] = px.c[1] = px.c[2] = 0;
@@ -161,16 +189,18 @@ __global__ void __launch_bounds__(128) two_view_augment_kernel(const uint8_t* __
       const double inv_x = (double)dw / v.cw, inv_y = (double)dh / v.ch;
       const double sc_x = 1.0 / inv_x, sc_y = 1.0 / inv_y;
       if (v.cw == dw && v.ch == dh) {  // same size: cv::resize copies
-        px = rotated_pixel(img, v, v.ox + dx, v.oy + dy);
+        px = rotated_pixel(img, v, v.ox + dx, v.oy + dy, row_term(v, v.oy + dy), cols);
       } else if (sc_x >= 1.0 && sc_y >= 1.0) {
         const int isx = __double2int_rn(sc_x), isy = __double2int_rn(sc_y);
         if (fabs(sc_x - isx) < 2.220446049250313e-16 && fabs(sc_y - isy) < 2.220446049250313e-16) {
           int sum[3] = {0, 0, 0};  // integer factors: plain box sum
-          for (int yy = 0; yy < isy; ++yy)
+          for (int yy = 0; yy < isy; ++yy) {
+            const RowTerm rt = row_term(v, v.oy + dy * isy + yy);
             for (int xx = 0; xx < isx; ++xx) {
-              const Px q = rotated_pixel(img, v, v.ox + dx * isx + xx, v.oy + dy * isy + yy);
+              const Px q = rotated_pixel(img, v, v.ox + dx * isx + xx, v.oy + dy * isy + yy, rt, cols);
               sum[0] += q.c[0], sum[1] += q.c[1], sum[2] += q.c[2];
             }
+          }
           const float scale = 1.f / (float)(isx * isy);
 #pragma unroll
           for (int k = 0; k < 3; ++k)
@@ -181,8 +211,9 @@ __global__ void __launch_bounds__(128) two_view_augment_kernel(const uint8_t* __
           float acc[3] = {0.f, 0.f, 0.f};
           for (int j = 0; j < cy.count; ++j) {
             float buf[3] = {0.f, 0.f, 0.f};
+            const RowTerm rt = row_term(v, v.oy + cy.first + j);
             for (int i = 0; i < cx.count; ++i) {
-              const Px q = rotated_pixel(img, v, v.ox + cx.first + i, v.oy + cy.first + j);
+              const Px q = rotated_pixel(img, v, v.ox + cx.first + i, v.oy + cy.first + j, rt, cols);
               const float al = area_weight(cx, i);
 #pragma unroll
               for (int k = 0; k < 3; ++k) buf[k] = __fadd_rn(buf[k], __fmul_rn((float)q.c[k], al));
@@ -200,8 +231,11 @@ __global__ void __launch_bounds__(128) two_view_augment_kernel(const uint8_t* __
         linear_coeff(dx, v.cw, sc_x, inv_x, &x0, &ax0, &ax1);
         linear_coeff(dy, v.ch, sc_y, inv_y, &y0, &by0, &by1);
         const int x1 = min(x0 + 1, v.cw - 1), y1 = min(y0 + 1, v.ch - 1);
-        const Px p00 = rotated_pixel(img, v, v.ox + x0, v.oy + y0), p01 = rotated_pixel(img, v, v.ox + x1, v.oy + y0);
-        const Px p10 = rotated_pixel(img, v, v.ox + x0, v.oy + y1), p11 = rotated_pixel(img, v, v.ox + x1, v.oy + y1);
+        const RowTerm r0 = row_term(v, v.oy + y0), r1 = row_term(v, v.oy + y1);
+        const Px p00 = rotated_pixel(img, v, v.ox + x0, v.oy + y0, r0, cols);
+        const Px p01 = rotated_pixel(img, v, v.ox + x1, v.oy + y0, r0, cols);
+        const Px p10 = rotated_pixel(img, v, v.ox + x0, v.oy + y1, r1, cols);
+        const Px p11 = rotated_pixel(img, v, v.ox + x1, v.oy + y1, r1, cols);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int h0 = p00.c[k] * ax0 + p01.c[k] * ax1, h1 = p10.c[k] * ax0 + p11.c[k] * ax1;
@@ -234,9 +268,10 @@ extern "C" int peclr_two_view_augment(const void* src_u8, long long src_bytes, c
   if (!src_u8 || !view_table || !out || n < 1 || n > 65535 || out_h < 1 || out_w < 1 || src_bytes < 1) return -1001;
   static_assert(sizeof(AugView) == 120, "parameter table row layout (gpu_augment.VIEW_DTYPE)");
   dim3 grid(out_h, n);
-  two_view_augment_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int cols_cap = 1024;  // crop columns whose fixed-point terms fit the block's shared-memory table (8 KB)
+  two_view_augment_kernel<<<grid, 128, cols_cap * sizeof(int2), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(src_u8), static_cast<const AugView*>(view_table), n, out_h, out_w, mean0, mean1,
-      mean2, std0, std1, std2, out, static_cast<uint8_t*>(stage_u8));
+      mean2, std0, std1, std2, out, static_cast<uint8_t*>(stage_u8), cols_cap);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

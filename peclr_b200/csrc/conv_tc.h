@@ -35,8 +35,8 @@ struct TapTable {
 
 void choose_box(int W, int H, int N, int target, int* bw, int* bh, int* bn);
 
-// Programmatic dependent launch for the kernels of the main stream's dependency chain (ptx.cuh: pdl_wait).
-// PECLR_PDL=0 launches them with plain stream serialization (A/B switch).
+// Programmatic dependent launch for the kernels of the main stream's dependency chain (ptx.cuh: pdl_wait), enabled
+// with PECLR_PDL=1.  Default off: measured slower on the full step (see pdl_enabled() in conv_tc.cu).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
