@@ -70,6 +70,18 @@ int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, i
 long long peclr_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
 int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, void* workspace, long long workspace_bytes, void* stream);
+/* The weight gradients of MANY convolutions with ONE ordered reduction (a ResNet stage's worth: the per-convolution
+ * reduction launches are mostly fixed cost): peclr_conv2d_wgrad_partials only writes the pixel splits' slabs
+ * (ksplit = peclr_conv2d_wgrad_splits(...) of them, each Cout*k*k*Cin floats, into its own workspace region; with
+ * ksplit == 1 it accumulates into dw directly and needs no row), then peclr_wgrad_reduce_batched adds, per table
+ * row {const float* partial; float* dw; int64 n4 (= elements / 4); int32 ksplit; int32 first_block}, the slabs to
+ * dw in slab order.  A row owns ceil(n4 / peclr_wgrad_reduce_block_f4()) consecutive blocks from first_block on;
+ * total_blocks is their sum.  `table` is a device array. */
+int peclr_conv2d_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int stride);
+int peclr_conv2d_wgrad_partials(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                                int k, int stride, void* workspace, long long workspace_bytes, void* stream);
+int peclr_wgrad_reduce_block_f4(void);
+int peclr_wgrad_reduce_batched(const void* table, int num_entries, int total_blocks, void* stream);
 /* 7x7/stride 2/pad 3 stem (features.0), computed as a 4x4/stride 1 convolution over 2x2 pixel blocks.
  * xpad = [N][H/2+3][W/2+4][16] bf16 from peclr_stem_input (space-to-depth, zero padded),
  * wpack = [64][4][4*16] bf16 from peclr_stem_pack, y = [N][H/2][W/2][64]. */

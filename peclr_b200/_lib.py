@@ -26,6 +26,10 @@ SIGNATURES = {
     "peclr_conv2d_dgrad_finish": [P, P, P, I, I, I, I, I, P, P, P, P],
     "peclr_conv2d_wgrad_workspace_bytes": [I, I, I, I, I, I, I],
     "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P, L, P],
+    "peclr_conv2d_wgrad_splits": [I, I, I, I, I, I, I],
+    "peclr_conv2d_wgrad_partials": [P, P, P, I, I, I, I, I, I, I, P, L, P],
+    "peclr_wgrad_reduce_block_f4": [],
+    "peclr_wgrad_reduce_batched": [P, I, I, P],
     "peclr_stem_fprop": [P, P, P, I, I, I, P, P, P],
     "peclr_stem_wgrad_workspace_bytes": [I, I, I],
     "peclr_stem_wgrad": [P, P, P, I, I, I, P, L, P],
@@ -61,7 +65,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"peclr_ntxent_workspace_bytes": c_longlong, "peclr_conv2d_wgrad_workspace_bytes": c_longlong,
              "peclr_stem_wgrad_workspace_bytes": c_longlong, "peclr_sgemm_workspace_bytes": c_longlong}
-_NO_CHECK = {"peclr_abi_version", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems",
+_NO_CHECK = {"peclr_abi_version", "peclr_ntxent_workspace_bytes", "peclr_opt_chunk_elems", "peclr_conv2d_wgrad_splits",
+             "peclr_wgrad_reduce_block_f4",
              "peclr_conv2d_wgrad_workspace_bytes", "peclr_stem_wgrad_workspace_bytes", "peclr_sgemm_workspace_bytes"}
 
 _ERRORS = {-1001: "bad argument", -1002: "CUDA driver entry point unavailable", -1003: "TMA tensor-map encoding failed"}
@@ -110,6 +115,8 @@ def _kernels_in_call(name, args):
         return 4 if (args[8] == 3 and args[9] == 2) else 1
     if name == "peclr_lars_adam_step":
         return 2 if args[17] else 1
+    if name == "peclr_conv2d_wgrad_partials":
+        return 1
     if name == "peclr_conv2d_wgrad":  # + the ordered reduction of the pixel splits
         return 2 if load().peclr_conv2d_wgrad_workspace_bytes(*args[3:10]) > 0 else 1
     if name == "peclr_stem_wgrad":

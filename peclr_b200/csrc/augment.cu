@@ -19,6 +19,8 @@
 // fly (each is 4 source taps): no intermediate image exists.  Launch-bound (a 128-sample batch of 224 x 224 sources
 // is 19 MB in, 25 MB out), so no shared-memory staging: the source taps of neighbouring threads hit L1 / L2.
 #include "../../include/peclr_b200.h"
+#include <math.h>
+
 #include "ptx.cuh"
 
 namespace peclr {
@@ -123,8 +125,12 @@ __device__ __forceinline__ void linear_coeff(int d, int ssize, double scale, dou
   *a1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(fx, 2048.f))));
 }
 
-__device__ __forceinline__ int sdiv_entry(int i) { return i ? __double2int_rn((double)(255 << 12) / (1.0 * i)) : 0; }
-__device__ __forceinline__ int hdiv_entry(int i) { return i ? __double2int_rn((double)(180 << 12) / (6.0 * i)) : 0; }
+// OpenCV's RGB2HSV_b division tables (hsv_shift 12): sdiv[i] = round((255 << 12) / i), hdiv[i] = round((180 << 12) /
+// (6 i)); filled once from the host (the same double-precision expression OpenCV evaluates).
+__constant__ int c_sdiv[256];
+__constant__ int c_hdiv[256];
+__device__ __forceinline__ int sdiv_entry(int i) { return c_sdiv[i]; }
+__device__ __forceinline__ int hdiv_entry(int i) { return c_hdiv[i]; }
 
 // color_jitter_sample on one 8-bit pixel (channel 0 plays "B", as the reference passes its RGB image to BGR2HSV)
 __device__ __forceinline__ Px color_jitter(Px p, const AugView& v) {
@@ -267,6 +273,19 @@ extern "C" int peclr_two_view_augment(const void* src_u8, long long src_bytes, c
                                       float std1, float std2, float* out, void* stage_u8, void* stream) {
   if (!src_u8 || !view_table || !out || n < 1 || n > 65535 || out_h < 1 || out_w < 1 || src_bytes < 1) return -1001;
   static_assert(sizeof(AugView) == 120, "parameter table row layout (gpu_augment.VIEW_DTYPE)");
+  static bool tables_ready = false;
+  if (!tables_ready) {
+    int sdiv[256], hdiv[256];
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; ++i) {
+      sdiv[i] = (int)nearbyint((double)(255 << 12) / (1.0 * i));
+      hdiv[i] = (int)nearbyint((double)(180 << 12) / (6.0 * i));
+    }
+    if (cudaMemcpyToSymbol(c_sdiv, sdiv, sizeof(sdiv)) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_hdiv, hdiv, sizeof(hdiv)) != cudaSuccess)
+      return -(int)cudaGetLastError();
+    tables_ready = true;
+  }
   dim3 grid(out_h, n);
   const int cols_cap = 1024;  // crop columns whose fixed-point terms fit the block's shared-memory table (8 KB)
   two_view_augment_kernel<<<grid, 128, cols_cap * sizeof(int2), static_cast<cudaStream_t>(stream)>>>(

@@ -262,6 +262,33 @@ extern "C" int peclr_conv2d_wgrad(const void* x, const void* dy, float* dw, int 
                            static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int peclr_conv2d_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int stride) {
+  TapTable taps;
+  int num_taps = 0;
+  View4 views[kMaxViews], d;
+  const int nv = wgrad_geometry(nullptr, nullptr, N, H, W, Cin, Cout, k, stride, views, &taps, &num_taps, &d);
+  if (nv < 0) return nv;
+  return conv_wgrad_splits(d, num_taps, Cin, Cout);
+}
+
+extern "C" int peclr_conv2d_wgrad_partials(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                                           int Cout, int k, int stride, void* workspace, long long workspace_bytes,
+                                           void* stream) {
+  TapTable taps;
+  int num_taps = 0;
+  View4 views[kMaxViews], d;
+  const int nv = wgrad_geometry(x, dy, N, H, W, Cin, Cout, k, stride, views, &taps, &num_taps, &d);
+  if (nv < 0) return nv;
+  return conv_wgrad_launch(views, nv, d, taps, num_taps, Cin, Cout, dw, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream), true);
+}
+
+extern "C" int peclr_wgrad_reduce_block_f4(void) { return wgrad_reduce_f4_per_block(); }
+
+extern "C" int peclr_wgrad_reduce_batched(const void* table, int num_entries, int total_blocks, void* stream) {
+  return wgrad_reduce_batched_launch(table, num_entries, total_blocks, static_cast<cudaStream_t>(stream));
+}
+
 // ---- 7x7 / stride 2 / pad 3 stem as a 4x4 / stride 1 convolution on the space-to-depth image ----------------
 // xs: [N][H/2 + 3][W/2 + 4][16] bf16 from peclr_stem_input (2 x 2 pixel blocks as 16-channel pixels, block (Y, X)
 // at (Y + 2, X + 2)).  out(oy, ox) = sum_{ty, tx < 4} w4[ty][tx] . xs(oy + ty, ox + tx): for output (oy, ox) and

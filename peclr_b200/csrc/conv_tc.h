@@ -78,6 +78,12 @@ bool conv_halo_enabled();
 // (conv_wgrad_workspace_bytes) and are added to dW in a fixed order by a second kernel.
 long long conv_wgrad_workspace_bytes(const View4& dy_view, int num_taps, int cin, int cout);
 int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view, const TapTable& taps, int num_taps,
-                      int cin, int cout, float* dw, void* workspace, long long workspace_bytes, cudaStream_t stream);
+                      int cin, int cout, float* dw, void* workspace, long long workspace_bytes, cudaStream_t stream,
+                      bool defer_reduce = false);
+// defer_reduce: only the pixel splits' slabs are written; the caller adds them to dW later, for many convolutions in
+// one launch (wgrad_reduce_batched_launch; table rows {partial, dw, n4, ksplit, first block}, see conv_tc.cu).
+int conv_wgrad_splits(const View4& dy_view, int num_taps, int cin, int cout);
+int wgrad_reduce_batched_launch(const void* table, int n, int total_blocks, cudaStream_t stream);
+int wgrad_reduce_f4_per_block();
 
 }  // namespace peclr

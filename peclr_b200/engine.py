@@ -47,6 +47,10 @@ class StepEngine:
         # block-output BatchNorm backward: the dgrad that completes a block input's gradient also masks it with the
         # previous block's ReLU bits and accumulates that block's BN-backward sums (peclr_conv2d_dgrad_finish)
         self.fuse_block_bn = os.environ.get("PECLR_FUSE_BLOCK_BN", "1") != "0"
+        # weight gradients: every convolution of a ResNet stage writes its pixel-split slabs into its own region of
+        # one workspace; ONE ordered reduction per stage adds them to the gradients (instead of one per convolution)
+        self.batch_wgrad_reduce = os.environ.get("PECLR_BATCH_WGRAD_REDUCE", "1") != "0"
+        self._wgrad_plans = {}
         self._side = None
         # workspaces of the split reductions (ordered, atomics-free: see include/peclr_b200.h).  The conv weight
         # gradients share one (they run in order on one stream), the stem's runs on the main stream and has its own;
@@ -363,7 +367,16 @@ class StepEngine:
         overlap = self.overlap_wgrad
         # size the weight-gradient workspace for the largest launch of this pass up front (on the main stream, so the
         # side stream never sees it reallocated under a running kernel)
-        self._wgrad_ws.get(self._max_wgrad_bytes(ctx), dev)
+        plan = self._wgrad_plan(ctx) if self.batch_wgrad_reduce else None
+        if plan is None:
+            self._wgrad_ws.get(self._max_wgrad_bytes(ctx), dev)
+
+        def conv_wgrad(conv, x, dy):
+            """dW of one convolution (enqueued through wgrad(): side stream)."""
+            if plan is None:
+                ops.conv2d_wgrad(x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"), ws=self._wgrad_ws)
+            else:
+                ops.conv2d_wgrad_partials(x, dy, conv.k, conv.stride, self._g(conv, "weight"), plan["region"][id(conv)])
 
         def wgrad(fn, *alive):
             if not overlap:
@@ -397,8 +410,7 @@ class StepEngine:
                 dy, g = ops.bn_backward(da, rec["mask"], y, sv, self._p(bn, "weight"), self._g(bn, "weight"),
                                         self._g(bn, "bias"), want_g=True, scratch=scratch, dy=da)
             da = None
-            wgrad(lambda x=x, dy=dy, conv=conv: ops.conv2d_wgrad(
-                x, dy, conv.k, conv.stride, dw=self._g(conv, "weight"), ws=self._wgrad_ws), x, dy)
+            wgrad(lambda x=x, dy=dy, conv=conv: conv_wgrad(conv, x, dy), x, dy)
             cur_hw = (x.shape[1], x.shape[2])
             for i in range(len(convs) - 1, 0, -1):
                 conv, bn, x, y, act, sv = convs[i]
@@ -414,8 +426,7 @@ class StepEngine:
                 dy = ops.bn_backward(dx, None, py, psv, self._p(pbn, "weight"), self._g(pbn, "weight"),
                                      self._g(pbn, "bias"), scratch=scratch, dy=dx, beta=self._p(pbn, "bias"),
                                      reduce_done=fused)
-                wgrad(lambda px=px, dy=dy, pconv=pconv: ops.conv2d_wgrad(
-                    px, dy, pconv.k, pconv.stride, dw=self._g(pconv, "weight"), ws=self._wgrad_ws), px, dy)
+                wgrad(lambda px=px, dy=dy, pconv=pconv: conv_wgrad(pconv, px, dy), px, dy)
             conv1 = convs[0][0]
             # the dgrad of conv1 completes the gradient of this block's input = the previous block's output
             prev = ctx["blocks"][bi - 1] if bi > 0 else None
@@ -427,8 +438,7 @@ class StepEngine:
                 dconv, dbn, yd, dsv = rec["down"]
                 dyd = ops.bn_backward(g, None, yd, dsv, self._p(dbn, "weight"), self._g(dbn, "weight"),
                                       self._g(dbn, "bias"), scratch=scratch, dy=g)
-                wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: ops.conv2d_wgrad(
-                    a_in, dyd, 1, dconv.stride, dw=self._g(dconv, "weight"), ws=self._wgrad_ws), a_in, dyd)
+                wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: conv_wgrad(dconv, a_in, dyd), a_in, dyd)
                 if finish:  # down-sampling branch first (its stride-2 form only touches a sub-lattice), conv1 finishes
                     da = ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride)
                     ops.conv2d_dgrad_finish(dy, self._wt(conv1), da, y_prev, prev["mask"], scratch)
@@ -444,8 +454,11 @@ class StepEngine:
                                      accumulate=True)
             if finish:
                 prev["prefinished"] = True
-            if after_stage is not None and (bi == 0 or stage_of[id(self.blocks[bi - 1])] != stage_of[id(blk)]):
-                after_stage(stage_of[id(blk)])
+            if bi == 0 or stage_of[id(self.blocks[bi - 1])] != stage_of[id(blk)]:
+                if plan is not None:  # this stage's weight gradients: one ordered reduction of all their slabs
+                    wgrad(lambda t=plan["tables"][stage_of[id(blk)]]: ops.wgrad_reduce_batched(t))
+                if after_stage is not None:
+                    after_stage(stage_of[id(blk)])
         # stem: max-pool + ReLU + BN backward, then the 7x7 weight gradient
         xpad, y0, sv0, pool_idx = ctx["stem"]
         h, w = ctx["hw"]
@@ -459,6 +472,38 @@ class StepEngine:
         keep.clear()
         if after_stage is not None:
             after_stage(-1)
+
+    def _wgrad_plan(self, ctx):
+        """Workspace regions (one per convolution with more than one pixel split) and the per-stage reduction tables
+        for this batch geometry.  Built once: the flat gradient buffer and the workspace do not move."""
+        key = (ctx["n"], ctx["hw"], self.grads.data_ptr())
+        if key in self._wgrad_plans:
+            return self._wgrad_plans[key]
+        f = self.encoder.features
+        stage_of = {id(blk): si for si, layer in enumerate((f[4], f[5], f[6], f[7])) for blk in layer}
+        items, total = [], 0
+        for blk, rec in zip(self.blocks, ctx["blocks"]):
+            shapes = [(conv, tuple(x.shape)) for conv, _, x, _, _, _ in rec["convs"]]
+            if "down" in rec:
+                shapes.append((rec["down"][0], tuple(rec["a_in"].shape)))
+            for conv, (n, h, w, cin) in shapes:
+                need = _lib.call("peclr_conv2d_wgrad_workspace_bytes", n, h, w, cin, conv.cout, conv.k, conv.stride)
+                ks = _lib.call("peclr_conv2d_wgrad_splits", n, h, w, cin, conv.cout, conv.k, conv.stride)
+                if need < 0 or ks < 1:
+                    raise _lib.PeclrKernelError("weight gradient: unsupported geometry")
+                items.append((stage_of[id(blk)], conv, need, ks, total))
+                total += (need + 255) // 256 * 256
+        buf = torch.empty((max(total, 256),), dtype=torch.uint8, device=self.device)
+        region, per_stage = {}, {0: [], 1: [], 2: [], 3: []}
+        for stage, conv, need, ks, off in items:
+            region[id(conv)] = buf[off:off + need] if need else None
+            if need:
+                s = self._seg(conv)
+                per_stage[stage].append((buf.data_ptr() + off, self.grads.data_ptr() + 4 * s.begin, s.size, ks))
+        tables = {st: ops.build_reduce_table(ent, self.device) for st, ent in per_stage.items()}
+        plan = {"buf": buf, "region": region, "tables": tables, "bytes": total}
+        self._wgrad_plans = {key: plan}  # (one geometry at a time: the workspace is GBs for the deep trunks)
+        return plan
 
     def _max_wgrad_bytes(self, ctx):
         key = (ctx["n"], ctx["hw"])

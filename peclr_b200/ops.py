@@ -131,6 +131,38 @@ def conv2d_wgrad(x, dy, k, stride, dw=None, ws=None):
     return dw
 
 
+REDUCE_DTYPE = np.dtype([("partial", "<i8"), ("dw", "<i8"), ("n4", "<i8"), ("ksplit", "<i4"), ("blk_begin", "<i4")])
+
+
+def conv2d_wgrad_partials(x, dy, k, stride, dw, ws_region):
+    """Weight gradient without its reduction: the pixel splits' slabs go to `ws_region` (uint8 tensor sized by
+    peclr_conv2d_wgrad_workspace_bytes; None when there is a single split, which accumulates into dw directly).  The
+    caller adds the slabs to dw later, for many convolutions at once (wgrad_reduce_batched)."""
+    _need_cuda(x, dy, dw)
+    n, h, wd, cin = x.shape
+    cout = dy.shape[-1]
+    _lib.call("peclr_conv2d_wgrad_partials", x, dy, dw, n, h, wd, cin, cout, k, stride, ws_region,
+              ws_region.numel() if ws_region is not None else 0, _s())
+
+
+def build_reduce_table(entries, device):
+    """entries: [(partial_ptr, dw_ptr, elements, ksplit)] -> (device table, rows, total blocks)."""
+    per_block = _lib.call("peclr_wgrad_reduce_block_f4")
+    tab = np.zeros(len(entries), dtype=REDUCE_DTYPE)
+    blocks = 0
+    for i, (pp, dp, n, ks) in enumerate(entries):
+        assert n % 4 == 0
+        tab[i] = (pp, dp, n // 4, ks, blocks)
+        blocks += (n // 4 + per_block - 1) // per_block
+    return torch.from_numpy(tab.view(np.uint8)).to(device), len(entries), blocks
+
+
+def wgrad_reduce_batched(table):
+    t, n, blocks = table
+    if n:
+        _lib.call("peclr_wgrad_reduce_batched", t, n, blocks, _s())
+
+
 def stem_input(img1, img2, out=None):
     """two fp32 NCHW batches -> zero-padded space-to-depth bf16 [2B, H/2+3, W/2+4, 16] (2x2 pixel blocks as
     16-channel pixels, block (Y, X) at (Y+2, X+2), channel = dy*6 + dx*3 + c)."""
