@@ -1,4 +1,4 @@
-"""Row bookkeeping of the data-parallel step: rank r holds B pairs; in the global 2*B*R batch NT-Xent sees,
+"""Test helper: row bookkeeping of the data-parallel step: rank r holds B pairs; in the global 2*B*R batch NT-Xent sees,
 view-1 rows of all ranks come first, then view-2 rows, so positives stay B*R apart.
 The CUDA kernel uses the same mapping (global_row in csrc/ntxent.cu)."""
 import numpy as np

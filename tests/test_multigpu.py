@@ -15,8 +15,9 @@ def _gloo_worker(rank, world, port, b, out):
     import torch.distributed as dist
 
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import peclr_oracle as po
-    from peclr_b200.dist_utils import global_rows, local_rows
+    from dist_rows import global_rows, local_rows
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -60,7 +61,7 @@ def test_global_batch_semantics_gloo(tmp_path):
 
 
 def test_row_mapping():
-    from peclr_b200.dist_utils import global_rows, local_rows
+    from dist_rows import global_rows, local_rows
 
     world, b = 4, 3
     seen = np.concatenate([global_rows(r, world, b) for r in range(world)])
