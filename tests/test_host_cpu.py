@@ -350,3 +350,24 @@ def test_batched_augmentation_parameters_equal_the_scalar_specification():
         assert np.array_equal(aug.table(scalar, b, 224, 240), aug.batch_table(bp, b, 224, 240))
     with pytest.raises(NotImplementedError):
         GpuTwoViewAugmenter(dict(resize=True, gaussian_blur=True))
+
+
+def test_stage_ranges_partition_the_flat_gradient_buffer(model):
+    """The per-stage all-reduce sends four contiguous ranges [stem + layer1 | layer2 | layer3 | layer4 + head] of the flat
+    gradient buffer, in the order backward finishes them (layer4 first): together they cover every trained scalar
+    exactly once and each boundary is a parameter boundary."""
+    ranges = model._stage_ranges()
+    assert set(ranges) == {3, 2, 1, -1}
+    spans = sorted(ranges.values())
+    assert spans[0][0] == 0 and spans[-1][1] == model.engine.total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    begins = {s.begin for s in model.engine.segs}
+    assert all(lo in begins for lo, _ in spans)
+    by_name = {s.name: s for s in model.engine.segs}
+    lo4, hi4 = ranges[3]
+    assert lo4 == by_name["encoder.features.7.0.conv1.weight"].begin and hi4 == model.engine.total
+    head = by_name["projection_head.0.weight"]
+    assert lo4 <= head.begin < hi4  # the head's gradients are final before the trunk's backward starts
+    assert ranges[-1] == (0, by_name["encoder.features.5.0.conv1.weight"].begin)
+    model.enable_overlapped_sync(True)  # one process: stays off
+    assert model._after_stage_hook is None
