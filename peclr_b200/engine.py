@@ -47,9 +47,12 @@ class StepEngine:
         # block-output BatchNorm backward: the dgrad that completes a block input's gradient also masks it with the
         # previous block's ReLU bits and accumulates that block's BN-backward sums (peclr_conv2d_dgrad_finish)
         self.fuse_block_bn = os.environ.get("PECLR_FUSE_BLOCK_BN", "1") != "0"
-        # weight gradients: every convolution of a ResNet stage writes its pixel-split slabs into its own region of
-        # one workspace; ONE ordered reduction per stage adds them to the gradients (instead of one per convolution)
-        self.batch_wgrad_reduce = os.environ.get("PECLR_BATCH_WGRAD_REDUCE", "1") != "0"
+        # weight gradients, optional: every convolution of a ResNet stage writes its pixel-split slabs into its own
+        # region of one workspace and ONE ordered reduction per stage adds them to the gradients (instead of one per
+        # convolution).  Measured SLOWER on B200 (same box: ResNet-50 17.55 vs 17.28 ms, ResNet-152 39.67 vs 38.85 ms):
+        # the slabs of a whole stage (0.3-2 GB) fall out of the L2 before they are read back, the per-convolution
+        # reduction finds much of its 30-40 MB still there.  Off by default; kept as a switch.
+        self.batch_wgrad_reduce = os.environ.get("PECLR_BATCH_WGRAD_REDUCE", "0") != "0"
         self._wgrad_plans = {}
         self._side = None
         # workspaces of the split reductions (ordered, atomics-free: see include/peclr_b200.h).  The conv weight
