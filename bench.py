@@ -329,7 +329,7 @@ def measure(ctx, model_size, batch, size, accumulate, steps, warmup, sample_cloc
            "clocks": sampler.summary() if sampler is not None else None, "micro_bytes": micro_bytes,
            "kernels_per_micro_step": graphed.kernels_per_replay if graphed is not None else None}
     del graphed, model, opt, sched, resident, host
-    torch.cuda.empty_cache()
+    _release()
     return res
 
 
@@ -420,6 +420,16 @@ def e2e_from_raw_images(ctx, model, opt, sched, batch, size, accumulate, steps, 
                      "the GPU (rotate, crop, INTER_AREA resize, HSV jitter, normalise) inside the timed region"}
 
 
+def _release():
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -449,7 +459,8 @@ def run_ours(args):
         probe.engine.world, probe.engine.rank = world, rank
         parity = dist_check.run_all(probe.engine, args.batch, world, rank, dev)
         del probe
-        torch.cuda.empty_cache()
+        _release()  # (symmetric-memory handles must be gone before a CUDA graph is captured: freeing them is not
+        # a capturable operation, and the model <-> engine reference cycle leaves that to the cyclic collector)
         if not parity["pass"]:
             if rank == 0:
                 print(json.dumps({"parity": parity, "error": "multi-GPU parity check failed"}))

@@ -182,6 +182,10 @@ def dp_step_parity(world, rank, dev, b=8, size=64, warm_steps=300):
         flag = _max_over_ranks(0.0 if (res["pass"] and same) else 1.0, dev) == 0.0
         res["pass"] = bool(flag)
         del ours, oracle
+        import gc
+
+        gc.collect()  # (the model <-> engine cycle holds a symmetric-memory handle: free it here, not during a capture)
+        torch.cuda.synchronize()
         torch.cuda.empty_cache()
         return res
     finally:
