@@ -27,7 +27,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 TOL_LOSS_REL, TOL_GRAD_REL = 1e-5, 1e-4       # fused loss kernel vs fp64 closed form
-TOL_DLOSS, TOL_COS_ALL, TOL_COS_TOP = 1.5e-3, 0.93, 0.985  # bf16 trunk step vs fp32 oracle
+TOL_DLOSS, TOL_COS_ALL, TOL_COS_TOP = 1e-2, 0.93, 0.985  # bf16 trunk step vs fp32 oracle at B = 8 per rank (tests/parity_util.py)
 
 
 def _max_over_ranks(x, dev):
