@@ -211,6 +211,10 @@ def test_bench_roofline_arithmetic():
     acc = ("peclr_conv2d_dgrad", (0, 0, 0, 256, 56, 56, 256, 64, 1, 1, 1, 0))
     plain = ("peclr_conv2d_dgrad", (0, 0, 0, 256, 56, 56, 256, 64, 1, 1, 0, 0))
     assert bench.conv_bytes(*acc) - bench.conv_bytes(*plain) == 2.0 * 256 * 56 * 56 * 256  # read-modify-write of dx
+    # the finishing dgrad (1x1): same FLOPs as the plain one; bytes = dy + weights + dx in and out + y + mask bits
+    fin = ("peclr_conv2d_dgrad_finish", (0, 0, 0, 256, 56, 56, 256, 64, 0, 0, 0, 0))
+    assert bench.conv_flops(*fin) == bench.conv_flops(*plain) and "peclr_conv2d_dgrad_finish" in bench.CONV_CALLS
+    assert bench.conv_bytes(*fin) == 2.0 * (256 * 56 * 56 * (3 * 256 + 64) + 256 * 64) + 256 * 56 * 56 * 256 / 8
     stem = ("peclr_stem_fprop", (0, 0, 0, 256, 224, 224, 0, 0, 0))
     assert bench.conv_flops(*stem) == 2.0 * 256 * 112 * 112 * 64 * 147
     # the whole ResNet-50 @ 224 figure of SURVEY 8(d) is 24.287 GFLOP per image: one 3x3 256->256 @14x14 is 0.2312 of it
