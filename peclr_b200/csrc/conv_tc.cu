@@ -93,14 +93,18 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   uint8_t* sB = sA + n_stages * stage_a;
   uint8_t* sD = sB + n_stages * stage_b;
   uint8_t* sY = sD + (BN / 64) * kStageA;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
-  uint8_t* sG = sY + (p.bn_reduce ? (BN / 64) * kStageA : 0);  // finish mode: the tile already in the output tensor
-  uint64_t* full = reinterpret_cast<uint64_t*>(sG + (p.bn_reduce == 2 ? (BN / 64) * kStageA : 0));
+  // finish mode: the tile already in the output tensor, DOUBLE buffered -- it is needed first (by the TMEM drain), and
+  // a single buffer exposed its load latency (~3000 clk of a ~6800 clk tile: the load could only be issued after the
+  // previous tile's drain)
+  uint8_t* sG = sY + (p.bn_reduce ? (BN / 64) * kStageA : 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sG + (p.bn_reduce == 2 ? 2 * (BN / 64) * kStageA : 0));
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* ybar = tempty + 2;  // [0] y tile landed, [1] y tile consumed
-  uint64_t* gbar = ybar + 2;    // [0] accumulated-gradient tile landed, [1] consumed (finish mode)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + 2);
+  uint64_t* gfull = ybar + 2;   // [b] accumulated-gradient tile landed in buffer b (finish mode)
+  uint64_t* gempty = gfull + 2; // [b] buffer b consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty + 2);
   // per-CTA statistics, one private copy per row group ([512/BN][2][cout]): every address has exactly one owner
   // thread, so the per-tile accumulation is a plain read-modify-write in a fixed order (reproducible; shared fp32
   // atomics are CAS loops and would add in arrival order).  When the copies do not fit next to the pipeline stages
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8 * CTAS);  // one arrival per epilogue warp (of both CTAs: the leader's barrier)
         mbar_init(&ybar[i], 1);
-        mbar_init(&gbar[i], 1);
+        mbar_init(&gfull[i], 1);
+        mbar_init(&gempty[i], 1);
       }
       fence_barrier_init();
     }
@@ -204,11 +209,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         if (p.bn_reduce == 2) {  // the gradient tile to add to (needed first, by the TMEM drain)
-          mbar_wait(&gbar[1], (tile_no & 1) ^ 1);
-          mbar_expect_tx(&gbar[0], (BN / 64) * kStageA);
+          const int gb = tile_no & 1;
+          mbar_wait(&gempty[gb], ((tile_no >> 1) & 1) ^ 1);
+          mbar_expect_tx(&gfull[gb], (BN / 64) * kStageA);
 #pragma unroll
           for (int bx = 0; bx < BN / 64; ++bx)
-            tma_load_4d(&p.d_map, &gbar[0], sG + bx * kStageA, nt * BN + bx * 64, w0, h0, n0);
+            tma_load_4d(&p.d_map, &gfull[gb], sG + (gb * (BN / 64) + bx) * kStageA, nt * BN + bx * 64, w0, h0, n0);
         }
         if (p.bn_reduce) {  // this tile's BN input, for the epilogue (own CTA, own barrier)
           mbar_wait(&ybar[1], (tile_no & 1) ^ 1);
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       const bool finish = p.bn_reduce == 2;
-      if (finish) mbar_wait(&gbar[0], it & 1);
+      if (finish) mbar_wait(&gfull[it & 1], (it >> 1) & 1);
       if (et == 0) tma_wait_group_read0();  // previous tile's TMA store has finished reading sD
       named_bar_sync(1, 256);
       long long mask_row = -1;  // finish mode: byte offset of this thread's pixel in the ReLU bit mask (-1: off-image)
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         if (finish) {
           // r += the tile already in the tensor (same swizzled position in sG as the store position in sD), then the
           // ReLU mask of the block output this is the gradient of: bit k of the word = channel (chunk * 32 + k)
-          const uint32_t gdelta = smem_u32(sG) - sD32;
+          const uint32_t gdelta = smem_u32(sG) + (it & 1) * (BN / 64) * kStageA - sD32;
           const uint32_t bits = mask_row >= 0
                                     ? *reinterpret_cast<const uint32_t*>(p.mask_bits + mask_row + ((nt * BN + chunk * 32) >> 3))
                                     : 0u;
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (et == 0) {
-        if (finish) mbar_arrive(&gbar[1]);  // every thread has read its part of sG: the producer may refill it
+        if (finish) mbar_arrive(&gempty[it & 1]);  // every thread has read its part of this sG buffer
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
           if (p.reduce_add)
@@ -823,7 +829,7 @@ template <int BN, int STAGES, int CTAS, bool HALO = false>
 static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
   constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
   // everything but the pipeline stages: alignment slack, output staging (+ y tile), barriers
-  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce == 2 ? 3 : (p.bn_reduce ? 2 : 1)) + 256;
+  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce == 2 ? 4 : (p.bn_reduce ? 2 : 1)) + 256;
   p.stat_copies = 0;
   if (stats) {
     p.stat_copies = 512 / BN;
@@ -974,9 +980,9 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
     if (BN == 64) return launch_gemm_t<64, 8, 2, true>(p, stats, stream);
     return PECLR_ERR_ARG;
   }
-  if (p.bn_reduce == 2) {  // three staging tiles (output, y, gradient-so-far): fewer pipeline stages
-    if (pairs) return launch_gemm_t<128, 4, 2>(p, stats, stream);
-    return launch_gemm_t<128, 3, 1>(p, stats, stream);
+  if (p.bn_reduce == 2) {  // four staging tiles (output, y, 2 x gradient-so-far): fewer pipeline stages
+    if (pairs) return launch_gemm_t<128, 3, 2>(p, stats, stream);
+    return launch_gemm_t<128, 2, 1>(p, stats, stream);
   }
   if (pairs) {
     if (BN == 256) return launch_gemm_t<256, 4, 2>(p, stats, stream);
