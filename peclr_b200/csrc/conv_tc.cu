@@ -71,6 +71,8 @@ struct GemmParams {
   // multiple of the 1024-byte swizzle atom).  Tap t's weights sit halo_kstep columns after tap t - 1's.
   int halo_taps, halo_kstep;
   int halo_a_bytes, halo_stage_a, halo_stages;
+  int n_stages;  // pipeline stages in use (<= the kernel's STAGES barriers)
+  int d_bufs;    // output staging tiles: 2 = tile i + 1 is drained while tile i's TMA store still reads its buffer
   int stat_copies;  // 512 / BN private copies of the per-CTA statistics (one owner thread per address), or 1 (the
                     // row groups then take turns on the single copy, in a fixed order)
 };
@@ -86,13 +88,14 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   // pipeline geometry: fixed for the per-tap kernels; in halo mode the A stage holds the taller box, the B stage
   // one weight tile per tap of the group, and the number of stages is whatever fits (<= STAGES barriers)
-  const int n_stages = HALO ? p.halo_stages : STAGES;
+  const int n_stages = p.n_stages;
   const uint32_t stage_a = HALO ? (uint32_t)p.halo_stage_a : (uint32_t)kStageA;
   const uint32_t stage_b = HALO ? (uint32_t)(p.halo_taps * kStageB) : (uint32_t)kStageB;
   uint8_t* sA = smem;
   uint8_t* sB = sA + n_stages * stage_a;
   uint8_t* sD = sB + n_stages * stage_b;
-  uint8_t* sY = sD + (BN / 64) * kStageA;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
+  constexpr uint32_t kTileD = (BN / 64) * kStageA;
+  uint8_t* sY = sD + p.d_bufs * kTileD;  // y tile of the fused BN-backward reduction (only if p.bn_reduce)
   // finish mode: the tile already in the output tensor, DOUBLE buffered -- it is needed first (by the TMEM drain), and
   // a single buffer exposed its load latency (~3000 clk of a ~6800 clk tile: the load could only be issued after the
   // previous tile's drain)
@@ -280,7 +283,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255
-    const uint32_t sD32 = smem_u32(sD);
     int it = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
@@ -290,11 +292,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       const int w0 = (mt % p.tiles_w) * p.Wb;
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
+      // output staging buffer of this tile; with two buffers the drain below only waits for the store of tile it - 2
+      uint8_t* sDt = sD + (p.d_bufs == 2 ? (it & 1) * kTileD : 0u);
+      const uint32_t sD32 = smem_u32(sDt);
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       const bool finish = p.bn_reduce == 2;
       if (finish) mbar_wait(&gfull[it & 1], (it >> 1) & 1);
-      if (et == 0) tma_wait_group_read0();  // previous tile's TMA store has finished reading sD
+      if (et == 0) {  // the TMA store that last used this buffer has finished reading it
+        if (p.d_bufs == 2) tma_wait_group_read1();
+        else tma_wait_group_read0();
+      }
       named_bar_sync(1, 256);
       long long mask_row = -1;  // finish mode: byte offset of this thread's pixel in the ReLU bit mask (-1: off-image)
       if (finish) {
@@ -355,9 +363,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
           if (p.reduce_add)
-            tma_reduce_add_4d(&p.d_map, sD + b * kStageA, nt * BN + b * 64, w0, h0, n0);
+            tma_reduce_add_4d(&p.d_map, sDt + b * kStageA, nt * BN + b * 64, w0, h0, n0);
           else
-            tma_store_4d(&p.d_map, sD + b * kStageA, nt * BN + b * 64, w0, h0, n0);
+            tma_store_4d(&p.d_map, sDt + b * kStageA, nt * BN + b * 64, w0, h0, n0);
         }
         tma_commit_group();
       }
@@ -825,11 +833,21 @@ static int sm_count() {
   return n;
 }
 
+static bool double_d_enabled() {  // PECLR_CONV_DOUBLE_D=0: single output staging tile (A/B runs)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PECLR_CONV_DOUBLE_D");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 template <int BN, int STAGES, int CTAS, bool HALO = false>
 static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
   constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
   // everything but the pipeline stages: alignment slack, output staging (+ y tile), barriers
-  size_t smem = 1024 + (size_t)(BN / 64) * kStageA * (p.bn_reduce == 2 ? 4 : (p.bn_reduce ? 2 : 1)) + 256;
+  const size_t tile_d = (size_t)(BN / 64) * kStageA;
+  size_t smem = 1024 + tile_d * (p.bn_reduce == 2 ? 4 : (p.bn_reduce ? 2 : 1)) + 256;
   p.stat_copies = 0;
   if (stats) {
     p.stat_copies = 512 / BN;
@@ -838,15 +856,24 @@ static int launch_gemm_t(GemmParams& p, bool stats, cudaStream_t stream) {
     if (smem + stages_min + (size_t)p.stat_copies * 2 * p.cout * 4 > kMaxSmem) p.stat_copies = 1;
     smem += (size_t)p.stat_copies * 2 * p.cout * 4;
   }
+  p.d_bufs = 1;
   if constexpr (HALO) {
     const size_t per_stage = (size_t)p.halo_stage_a + (size_t)p.halo_taps * (BN / CTAS) * 128;
     int stages = (int)((kMaxSmem - smem) / per_stage);
     if (stages > STAGES) stages = STAGES;
     if (stages < 2) return PECLR_ERR_ARG;
-    p.halo_stages = stages;
+    p.halo_stages = p.n_stages = stages;
     smem += (size_t)stages * per_stage;
   } else {
-    smem += (size_t)STAGES * (kStageA + (BN / CTAS) * 128);
+    const size_t per_stage = kStageA + (BN / CTAS) * 128;
+    p.n_stages = STAGES;
+    // a second output staging tile only where it costs no pipeline stage: per-launch A/B (profiles/ab_r02.txt) shows
+    // -0.5 us on the launches that keep their stages and +2..10 us on the ones that gave up two of six
+    if (double_d_enabled() && smem + tile_d + (size_t)STAGES * per_stage <= kMaxSmem) {
+      p.d_bufs = 2;
+      smem += tile_d;
+    }
+    smem += (size_t)p.n_stages * per_stage;
   }
   if (smem > kMaxSmem) return PECLR_ERR_ARG;
   auto kern = conv_gemm_kernel<BN, STAGES, CTAS, HALO>;

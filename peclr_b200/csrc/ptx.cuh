@@ -98,6 +98,9 @@ __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_wait_group_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
+__device__ __forceinline__ void tma_wait_group_read1() {  // all but the most recent bulk group have read their source
+  asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+}
 __device__ __forceinline__ void tma_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
