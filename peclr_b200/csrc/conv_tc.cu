@@ -35,6 +35,28 @@ namespace peclr {
 
 constexpr int kStageA = 128 * 128;  // 128 pixel rows x 64 bf16
 
+// Division by a launch constant as multiply-high + shift (exact for 0 <= x < 2^31): the tile -> (w, h, n) arithmetic
+// sits at the head of every tile's critical path in all three warp roles, and a hardware integer division is a
+// ~25-instruction dependent chain through the reciprocal unit.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, d};
+  if (d > 1) {
+    int lg = 31 - __builtin_clz((unsigned)d);
+    if (d & (d - 1)) ++lg;  // ceil(log2 d)
+    const int sh = 31 + lg;
+    f.mul = (uint32_t)(((1ull << sh) + (unsigned)d - 1) / (unsigned)d);
+    f.shr = (uint32_t)(sh - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ int fd_div(const FastDiv& f, int x) {
+  return f.d == 1 ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
+}
+
 struct GemmParams {
   CUtensorMap a_maps[kMaxViews];
   CUtensorMap b_map;
@@ -42,6 +64,7 @@ struct GemmParams {
   TapTable taps;
   int num_taps, c_chunks;
   int tiles_w, tiles_h, tiles_n, n_tiles;
+  FastDiv fd_tiles_w, fd_tiles_h, fd_n_tiles;
   int Wb, Hb, Nb;
   int log_wb, log_wbhb;
   int d_w, d_h, d_n;
@@ -165,11 +188,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       uint32_t phase = 0;
       int tile_no = 0;
       for (int t = first_tile; t < total_tiles; t += tile_step, ++tile_no) {
-        const int nt = t % p.n_tiles;
-        const int mt = (t / p.n_tiles) * CTAS + cta_rank;  // may be one past the end: all-OOB boxes (zero fill)
-        const int w0 = (mt % p.tiles_w) * p.Wb;
-        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
+        const int tq = fd_div(p.fd_n_tiles, t);
+        const int nt = t - tq * p.n_tiles;
+        const int mt = tq * CTAS + cta_rank;  // may be one past the end: all-OOB boxes (zero fill)
+        const int mq = fd_div(p.fd_tiles_w, mt), nq = fd_div(p.fd_tiles_h, mq);
+        const int w0 = (mt - mq * p.tiles_w) * p.Wb;
+        const int h0 = (mq - nq * p.tiles_h) * p.Hb;
+        const int n0 = nq * p.Nb;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const CUtensorMap* amap = &p.a_maps[p.taps.view[tap]];
           const int cw = w0 + p.taps.dw[tap];
@@ -287,30 +312,39 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = t % p.n_tiles;
-      const int mt = (t / p.n_tiles) * CTAS + cta_rank;
-      const int w0 = (mt % p.tiles_w) * p.Wb;
-      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Hb;
-      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nb;
+      const int tq = fd_div(p.fd_n_tiles, t);
+      const int nt = t - tq * p.n_tiles;
+      const int mt = tq * CTAS + cta_rank;
+      const int mq = fd_div(p.fd_tiles_w, mt), nq = fd_div(p.fd_tiles_h, mq);
+      const int w0 = (mt - mq * p.tiles_w) * p.Wb;
+      const int h0 = (mq - nq * p.tiles_h) * p.Hb;
+      const int n0 = nq * p.Nb;
       // output staging buffer of this tile; with two buffers the drain below only waits for the store of tile it - 2
       uint8_t* sDt = sD + (p.d_bufs == 2 ? (it & 1) * kTileD : 0u);
       const uint32_t sD32 = smem_u32(sDt);
+      const bool finish = p.bn_reduce == 2;
+      // finish mode: this thread's ReLU-mask words (one per column chunk), fetched before anything is waited for --
+      // issued at the point of use, the global load was the largest single stall of the kernel (14 % of all samples)
+      uint32_t mask_word[BN / 64];
+      if (finish) {
+        const int wl = row & (p.Wb - 1), hl = (row >> p.log_wb) & (p.Hb - 1), nl = row >> p.log_wbhb;
+        const bool on_image = w0 + wl < p.d_w && h0 + hl < p.d_h && n0 + nl < p.d_n;
+        const long long mask_row = (p.pix_base + (long long)(w0 + wl) * p.pix_w + (long long)(h0 + hl) * p.pix_h +
+                                    (long long)(n0 + nl) * p.pix_n) * p.mask_row_bytes;
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci)
+          mask_word[ci] = on_image ? *reinterpret_cast<const uint32_t*>(
+                                         p.mask_bits + mask_row + ((nt * BN + (half * (BN / 64) + ci) * 32) >> 3))
+                                   : 0u;  // off-image rows: the TMA store clips them, the statistics must not see them
+      }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
-      const bool finish = p.bn_reduce == 2;
       if (finish) mbar_wait(&gfull[it & 1], (it >> 1) & 1);
       if (et == 0) {  // the TMA store that last used this buffer has finished reading it
         if (p.d_bufs == 2) tma_wait_group_read1();
         else tma_wait_group_read0();
       }
       named_bar_sync(1, 256);
-      long long mask_row = -1;  // finish mode: byte offset of this thread's pixel in the ReLU bit mask (-1: off-image)
-      if (finish) {
-        const int wl = row & (p.Wb - 1), hl = (row >> p.log_wb) & (p.Hb - 1), nl = row >> p.log_wbhb;
-        if (w0 + wl < p.d_w && h0 + hl < p.d_h && n0 + nl < p.d_n)
-          mask_row = (p.pix_base + (long long)(w0 + wl) * p.pix_w + (long long)(h0 + hl) * p.pix_h +
-                      (long long)(n0 + nl) * p.pix_n) * p.mask_row_bytes;
-      }
 #pragma unroll
       for (int ci = 0; ci < BN / 64; ++ci) {
         const int chunk = half * (BN / 64) + ci;
@@ -322,9 +356,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           // r += the tile already in the tensor (same swizzled position in sG as the store position in sD), then the
           // ReLU mask of the block output this is the gradient of: bit k of the word = channel (chunk * 32 + k)
           const uint32_t gdelta = smem_u32(sG) + (it & 1) * (BN / 64) * kStageA - sD32;
-          const uint32_t bits = mask_row >= 0
-                                    ? *reinterpret_cast<const uint32_t*>(p.mask_bits + mask_row + ((nt * BN + chunk * 32) >> 3))
-                                    : 0u;
+          const uint32_t bits = mask_word[ci];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c16 = (chunk & 1) * 4 + j;
@@ -570,10 +602,14 @@ __global__ void __maxnreg__(80) conv_wgrad_kernel(const __grid_constant__ WgradP
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // pixel-chunk coordinates advance incrementally (one division set per CTA, none per pipeline stage)
+      int tw = c_begin % p.tiles_w, th = (c_begin / p.tiles_w) % p.tiles_h, tn = c_begin / (p.tiles_w * p.tiles_h);
       for (int c = c_begin; c < c_end; ++c) {
-        const int w0 = (c % p.tiles_w) * p.Wb;
-        const int h0 = ((c / p.tiles_w) % p.tiles_h) * p.Hb;
-        const int n0 = (c / (p.tiles_w * p.tiles_h)) * p.Nb;
+        const int w0 = tw * p.Wb, h0 = th * p.Hb, n0 = tn * p.Nb;
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) th = 0, ++tn;
+        }
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty[stage], phase ^ 1);
         int a_box_count = ntap * p.a_boxes;
@@ -687,6 +723,38 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restr
       acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
     dw[i] = acc;
+  }
+}
+
+// Few elements, many slabs (the 1x1 convolutions of the first stages: 4096 float4 x ~100 slabs): one thread per
+// element would walk the slabs as one long chain of dependent loads (26 us for a 64 KB gradient).  Here S warps-rows of
+// a block share each element: row s adds slabs s, s + S, ... (coalesced across the row), the S partial sums meet in
+// shared memory and are added in row order -- a fixed order again, so the result stays bit-reproducible.
+template <int S>
+__global__ void __launch_bounds__(256) wgrad_reduce_split_kernel(const float4* __restrict__ partial, float4* dw,
+                                                                 int64_t n4, int ksplit) {
+  constexpr int kPos = 256 / S;
+  __shared__ float4 part[S][kPos];
+  const int s_row = threadIdx.x / kPos, col = threadIdx.x % kPos;
+  const int64_t i = (int64_t)blockIdx.x * kPos + col;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+#pragma unroll 4
+    for (int ks = s_row; ks < ksplit; ks += S) {
+      const float4 v = __ldcs(partial + (int64_t)ks * n4 + i);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  }
+  part[s_row][col] = acc;
+  __syncthreads();
+  if (s_row == 0 && i < n4) {
+    float4 out = dw[i];
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+      const float4 v = part[r][col];
+      out.x += v.x, out.y += v.y, out.z += v.z, out.w += v.w;
+    }
+    dw[i] = out;
   }
 }
 
@@ -997,6 +1065,7 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
   p.tiles_h = (int)((d_view.h + bh - 1) / bh);
   p.tiles_n = (int)((d_view.n + bn - 1) / bn);
   p.n_tiles = (int)(nout / BN);
+  p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h), p.fd_n_tiles = make_fastdiv(p.n_tiles);
   p.cout = (int)nout;
   p.stat_sum = stat_sum;
   p.stat_sumsq = stat_sumsq;
@@ -1132,9 +1201,23 @@ int conv_wgrad_launch(const View4* x_views, int num_views, const View4& dy_view,
   if (rc || p.ksplit == 1 || defer_reduce) return rc;
   const int64_t n4 = p.partial_stride / 4;
   int64_t blocks = (n4 + 255) / 256;
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(p.partial),
-                                                       reinterpret_cast<float4*>(dw), n4, p.ksplit);
+  const float4* part = reinterpret_cast<const float4*>(p.partial);
+  float4* out = reinterpret_cast<float4*>(dw);
+  // share each element among S thread rows while that still fills the machine and leaves every row >= 4 slabs
+  int S = 1;
+  while (S < 16 && blocks * (2 * S) <= 2 * sm_count() && p.ksplit >= 8 * S) S *= 2;
+  if (S == 1) {
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(part, out, n4, p.ksplit);
+  } else if (S == 2) {
+    wgrad_reduce_split_kernel<2><<<(int)((n4 + 127) / 128), 256, 0, stream>>>(part, out, n4, p.ksplit);
+  } else if (S == 4) {
+    wgrad_reduce_split_kernel<4><<<(int)((n4 + 63) / 64), 256, 0, stream>>>(part, out, n4, p.ksplit);
+  } else if (S == 8) {
+    wgrad_reduce_split_kernel<8><<<(int)((n4 + 31) / 32), 256, 0, stream>>>(part, out, n4, p.ksplit);
+  } else {
+    wgrad_reduce_split_kernel<16><<<(int)((n4 + 15) / 16), 256, 0, stream>>>(part, out, n4, p.ksplit);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

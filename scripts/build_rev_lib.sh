@@ -14,7 +14,7 @@ git -C "$root" show "$rev:include/peclr_b200.h" > "$tmp/include/peclr_b200.h"
 objs=""
 for src in "$tmp"/peclr_b200/csrc/*.cu; do
   fast="--use_fast_math"
-  case "$(basename "$src")" in ntxent.cu|equiv_ops.cu|lars_adam.cu|head.cu|bn_act.cu) fast="";; esac
+  case "$(basename "$src")" in ntxent.cu|equiv_ops.cu|lars_adam.cu|head.cu|bn_act.cu|rn25d_head.cu|augment.cu) fast="";; esac
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $fast -c "$src" -o "${src%.cu}.o" &
   objs="$objs ${src%.cu}.o"
 done
