@@ -308,6 +308,30 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255
+    // finish mode: this thread's ReLU-mask words (one per column chunk) of tile t.  They are fetched ONE TILE AHEAD:
+    // issued at the point of use, this global load was the largest single stall of the kernel (14 % of all samples),
+    // and still 9 % when issued at the top of its own tile.
+    const bool finish = p.bn_reduce == 2;
+    auto fetch_mask = [&](int t, uint32_t* words) {
+      const int tq = fd_div(p.fd_n_tiles, t);
+      const int nt = t - tq * p.n_tiles;
+      const int mt = tq * CTAS + cta_rank;
+      const int mq = fd_div(p.fd_tiles_w, mt), nq = fd_div(p.fd_tiles_h, mq);
+      const int w = (mt - mq * p.tiles_w) * p.Wb + (row & (p.Wb - 1));
+      const int h = (mq - nq * p.tiles_h) * p.Hb + ((row >> p.log_wb) & (p.Hb - 1));
+      const int n = nq * p.Nb + (row >> p.log_wbhb);
+      // off-image rows: the TMA store clips them, the statistics must not see them
+      const bool on_image = t < total_tiles && w < p.d_w && h < p.d_h && n < p.d_n;
+      const long long mask_row =
+          (p.pix_base + (long long)w * p.pix_w + (long long)h * p.pix_h + (long long)n * p.pix_n) * p.mask_row_bytes;
+#pragma unroll
+      for (int ci = 0; ci < BN / 64; ++ci)
+        words[ci] = on_image ? *reinterpret_cast<const uint32_t*>(p.mask_bits + mask_row +
+                                                                  ((nt * BN + (half * (BN / 64) + ci) * 32) >> 3))
+                             : 0u;
+    };
+    uint32_t mask_next[BN / 64];
+    if (finish) fetch_mask(first_tile, mask_next);
     int it = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
@@ -322,20 +346,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       // output staging buffer of this tile; with two buffers the drain below only waits for the store of tile it - 2
       uint8_t* sDt = sD + (p.d_bufs == 2 ? (it & 1) * kTileD : 0u);
       const uint32_t sD32 = smem_u32(sDt);
-      const bool finish = p.bn_reduce == 2;
-      // finish mode: this thread's ReLU-mask words (one per column chunk), fetched before anything is waited for --
-      // issued at the point of use, the global load was the largest single stall of the kernel (14 % of all samples)
       uint32_t mask_word[BN / 64];
       if (finish) {
-        const int wl = row & (p.Wb - 1), hl = (row >> p.log_wb) & (p.Hb - 1), nl = row >> p.log_wbhb;
-        const bool on_image = w0 + wl < p.d_w && h0 + hl < p.d_h && n0 + nl < p.d_n;
-        const long long mask_row = (p.pix_base + (long long)(w0 + wl) * p.pix_w + (long long)(h0 + hl) * p.pix_h +
-                                    (long long)(n0 + nl) * p.pix_n) * p.mask_row_bytes;
 #pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci)
-          mask_word[ci] = on_image ? *reinterpret_cast<const uint32_t*>(
-                                         p.mask_bits + mask_row + ((nt * BN + (half * (BN / 64) + ci) * 32) >> 3))
-                                   : 0u;  // off-image rows: the TMA store clips them, the statistics must not see them
+        for (int ci = 0; ci < BN / 64; ++ci) mask_word[ci] = mask_next[ci];
+        fetch_mask(t + tile_step, mask_next);
       }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
@@ -402,26 +417,33 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         tma_commit_group();
       }
       if (want_stats) {
-        // column sums of the bf16 values just staged (exactly what the next kernels will read).  Thread =
-        // one column pair x one contiguous row range; shared-space 32-bit loads, 8 rows in flight.
-        constexpr int kPairs = BN / 2;
-        constexpr int kRowGroups = 256 / kPairs;
-        constexpr int kRowsPer = 128 / kRowGroups;
-        const int pair = et % kPairs;
-        const int rg = et / kPairs;
-        const int col = pair * 2;
+        // column sums of the bf16 values just staged (exactly what the next kernels will read).  A thread owns four
+        // adjacent columns (one 8-byte shared load per row) and a contiguous row range; the two half-warps of a warp
+        // read two different rows (a full 128-byte line each: conflict free) and meet through one shuffle.  The
+        // arithmetic runs on packed fp32 pairs: this loop is half of the epilogue's instructions, and the epilogue is
+        // the critical path of the wide 1x1 convolutions.
+        constexpr int kQuadWarps = BN / 64;            // warps that together span the BN columns
+        constexpr int kRowGroups = 2 * (8 / kQuadWarps);  // = 1024 / BN
+        constexpr int kRowsPer = 128 / kRowGroups;        // = BN / 8
+        const int ew = et >> 5;                            // epilogue warp 0..7
+        const int copy = ew / kQuadWarps;                  // statistics copy (of 512 / BN) this warp adds to
+        const int rg = copy * 2 + (lane >> 4);
+        const int col = ((ew % kQuadWarps) * 16 + (lane & 15)) * 4;
         const int c16 = (col & 63) >> 3;
-        const uint32_t base = sD32 + (col >> 6) * kStageA + ((col & 7) << 1) + rg * kRowsPer * 128;
+        const uint32_t base = sD32 + (col >> 6) * kStageA + ((col & 4) << 1) + rg * kRowsPer * 128;
         const uint32_t ydelta = smem_u32(sY) - sD32;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
-        float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
+        float2 s01[2] = {{0.f, 0.f}, {0.f, 0.f}}, s23[2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float2 q01[2] = {{0.f, 0.f}, {0.f, 0.f}}, q23[2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float2 sc01 = {0.f, 0.f}, sc23 = {0.f, 0.f}, sh01 = {0.f, 0.f}, sh23 = {0.f, 0.f};
         if (p.bn_reduce == 2) mbar_wait(&ybar[0], it & 1);
         if (p.bn_reduce == 1) {
           const int ch = nt * BN + col;
-          sc0 = p.bn_gamma[ch] * p.bn_invstd[ch];
-          sh0 = p.bn_beta[ch] - p.bn_mean[ch] * sc0;
-          sc1 = p.bn_gamma[ch + 1] * p.bn_invstd[ch + 1];
-          sh1 = p.bn_beta[ch + 1] - p.bn_mean[ch + 1] * sc1;
+          // (scalar loads: gamma / beta are views into the flat parameter buffer, not necessarily 16-byte aligned)
+          sc01 = make_float2(p.bn_gamma[ch] * p.bn_invstd[ch], p.bn_gamma[ch + 1] * p.bn_invstd[ch + 1]);
+          sc23 = make_float2(p.bn_gamma[ch + 2] * p.bn_invstd[ch + 2], p.bn_gamma[ch + 3] * p.bn_invstd[ch + 3]);
+          sh01 = make_float2(p.bn_beta[ch] - p.bn_mean[ch] * sc01.x, p.bn_beta[ch + 1] - p.bn_mean[ch + 1] * sc01.y);
+          sh23 = make_float2(p.bn_beta[ch + 2] - p.bn_mean[ch + 2] * sc23.x,
+                             p.bn_beta[ch + 3] - p.bn_mean[ch + 3] * sc23.y);
           mbar_wait(&ybar[0], it & 1);
         }
         // rows of a box that hangs over the image edge are clipped by the TMA store: keep them out of the
@@ -429,67 +451,67 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         const bool edge = w0 + p.Wb > p.d_w || h0 + p.Hb > p.d_h || n0 + p.Nb > p.d_n;
 #pragma unroll 2
         for (int r8 = 0; r8 < kRowsPer / 8; ++r8) {
-          uint32_t v[8];
+          uint2 v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = lds_u32(base + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
+          for (int j = 0; j < 8; ++j) v[j] = lds_v2(base + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
           if (edge) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int r0 = rg * kRowsPer + r8 * 8 + j;
               const int wl = r0 & (p.Wb - 1), hl = (r0 >> p.log_wb) & (p.Hb - 1), nl = r0 >> p.log_wbhb;
-              if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) v[j] = 0u;
+              if (w0 + wl >= p.d_w || h0 + hl >= p.d_h || n0 + nl >= p.d_n) v[j] = make_uint2(0u, 0u);
             }
-          }
-          if (p.bn_reduce == 2) {  // the staged values are the masked gradient already
-            uint32_t u[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = lds_u32(base + ydelta + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float a0 = bf16_lo(v[j]), b0 = bf16_hi(v[j]), a1 = bf16_lo(v[j + 1]), b1 = bf16_hi(v[j + 1]);
-              s0 += a0, s1 += b0, s2 += a1, s3 += b1;
-              q0 = fmaf(a0, bf16_lo(u[j]), q0), q1 = fmaf(b0, bf16_hi(u[j]), q1);
-              q2 = fmaf(a1, bf16_lo(u[j + 1]), q2), q3 = fmaf(b1, bf16_hi(u[j + 1]), q3);
-            }
-            continue;
           }
           if (p.bn_reduce) {
-            uint32_t u[8];
+            uint2 u[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = lds_u32(base + ydelta + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
+            for (int j = 0; j < 8; ++j) u[j] = lds_v2(base + ydelta + r8 * 1024 + j * 128 + ((c16 ^ j) << 4));
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float y0 = bf16_lo(u[j]), y1 = bf16_hi(u[j]), y2 = bf16_lo(u[j + 1]), y3 = bf16_hi(u[j + 1]);
-              const float a0 = fmaf(y0, sc0, sh0) > 0.f ? bf16_lo(v[j]) : 0.f;
-              const float b0 = fmaf(y1, sc1, sh1) > 0.f ? bf16_hi(v[j]) : 0.f;
-              const float a1 = fmaf(y2, sc0, sh0) > 0.f ? bf16_lo(v[j + 1]) : 0.f;
-              const float b1 = fmaf(y3, sc1, sh1) > 0.f ? bf16_hi(v[j + 1]) : 0.f;
-              s0 += a0, s1 += b0, s2 += a1, s3 += b1;
-              q0 = fmaf(a0, y0, q0), q1 = fmaf(b0, y1, q1), q2 = fmaf(a1, y2, q2), q3 = fmaf(b1, y3, q3);
+            for (int j = 0; j < 8; ++j) {
+              const float2 y01 = bf16x2_f2(u[j].x), y23 = bf16x2_f2(u[j].y);
+              float2 g01 = bf16x2_f2(v[j].x), g23 = bf16x2_f2(v[j].y);
+              if (p.bn_reduce == 1) {  // the gradient passes where the recomputed BN + ReLU output is positive
+                const float2 t01 = ffma2(y01, sc01, sh01), t23 = ffma2(y23, sc23, sh23);
+                g01.x = t01.x > 0.f ? g01.x : 0.f, g01.y = t01.y > 0.f ? g01.y : 0.f;
+                g23.x = t23.x > 0.f ? g23.x : 0.f, g23.y = t23.y > 0.f ? g23.y : 0.f;
+              }  // (mode 2: the staged values are the masked gradient already)
+              s01[j & 1] = fadd2(s01[j & 1], g01), s23[j & 1] = fadd2(s23[j & 1], g23);
+              q01[j & 1] = ffma2(g01, y01, q01[j & 1]), q23[j & 1] = ffma2(g23, y23, q23[j & 1]);
             }
             continue;
           }
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float a0 = bf16_lo(v[j]), b0 = bf16_hi(v[j]);
-            const float a1 = bf16_lo(v[j + 1]), b1 = bf16_hi(v[j + 1]);
-            s0 += a0, s1 += b0, s2 += a1, s3 += b1;
-            q0 = fmaf(a0, a0, q0), q1 = fmaf(b0, b0, q1), q2 = fmaf(a1, a1, q2), q3 = fmaf(b1, b1, q3);
+          for (int j = 0; j < 8; ++j) {
+            const float2 x01 = bf16x2_f2(v[j].x), x23 = bf16x2_f2(v[j].y);
+            s01[j & 1] = fadd2(s01[j & 1], x01), s23[j & 1] = fadd2(s23[j & 1], x23);
+            q01[j & 1] = ffma2(x01, x01, q01[j & 1]), q23[j & 1] = ffma2(x23, x23, q23[j & 1]);
           }
         }
+        // even + odd rows, then lower + upper half-warp (a fixed order), then one owner thread per address
+        float4 ts, tq;
+        ts.x = s01[0].x + s01[1].x, ts.y = s01[0].y + s01[1].y, ts.z = s23[0].x + s23[1].x, ts.w = s23[0].y + s23[1].y;
+        tq.x = q01[0].x + q01[1].x, tq.y = q01[0].y + q01[1].y, tq.z = q23[0].x + q23[1].x, tq.w = q23[0].y + q23[1].y;
+        ts.x += __shfl_down_sync(0xffffffffu, ts.x, 16), ts.y += __shfl_down_sync(0xffffffffu, ts.y, 16);
+        ts.z += __shfl_down_sync(0xffffffffu, ts.z, 16), ts.w += __shfl_down_sync(0xffffffffu, ts.w, 16);
+        tq.x += __shfl_down_sync(0xffffffffu, tq.x, 16), tq.y += __shfl_down_sync(0xffffffffu, tq.y, 16);
+        tq.z += __shfl_down_sync(0xffffffffu, tq.z, 16), tq.w += __shfl_down_sync(0xffffffffu, tq.w, 16);
         if (p.stat_copies > 1) {
-          float2* mine_s = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + nt * BN + col);
-          float2* mine_q = reinterpret_cast<float2*>(sStat + (size_t)rg * 2 * p.cout + p.cout + nt * BN + col);
-          float2 as = *mine_s, aq = *mine_q;
-          as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
-          *mine_s = as, *mine_q = aq;
+          if (lane < 16) {
+            float4* mine_s = reinterpret_cast<float4*>(sStat + (size_t)copy * 2 * p.cout + nt * BN + col);
+            float4* mine_q = reinterpret_cast<float4*>(sStat + (size_t)copy * 2 * p.cout + p.cout + nt * BN + col);
+            float4 as = *mine_s, aq = *mine_q;
+            as.x += ts.x, as.y += ts.y, as.z += ts.z, as.w += ts.w;
+            aq.x += tq.x, aq.y += tq.y, aq.z += tq.z, aq.w += tq.w;
+            *mine_s = as, *mine_q = aq;
+          }
         } else {
-          for (int g = 0; g < kRowGroups; ++g) {  // fixed order: row group 0 first
-            if (rg == g) {
-              float2* mine_s = reinterpret_cast<float2*>(sStat + nt * BN + col);
-              float2* mine_q = reinterpret_cast<float2*>(sStat + p.cout + nt * BN + col);
-              float2 as = *mine_s, aq = *mine_q;
-              as.x += s0 + s2, as.y += s1 + s3, aq.x += q0 + q2, aq.y += q1 + q3;
+          for (int g = 0; g < 512 / BN; ++g) {  // fixed order: copy 0's rows first
+            if (copy == g && lane < 16) {
+              float4* mine_s = reinterpret_cast<float4*>(sStat + nt * BN + col);
+              float4* mine_q = reinterpret_cast<float4*>(sStat + p.cout + nt * BN + col);
+              float4 as = *mine_s, aq = *mine_q;
+              as.x += ts.x, as.y += ts.y, as.z += ts.z, as.w += ts.w;
+              aq.x += tq.x, aq.y += tq.y, aq.z += tq.z, aq.w += tq.w;
               *mine_s = as, *mine_q = aq;
             }
             named_bar_sync(3, 256);

@@ -257,6 +257,32 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100: one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 bf16x2_f2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
