@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
                                                                 uint8_t* __restrict__ idx_out, float* mean_out,
                                                                 float* invstd_out, float* running_mean,
                                                                 float* running_var, int N, int H, int W, float eps,
-                                                                float momentum) {
+                                                                float momentum, FastDiv fd_wo, FastDiv fd_ho) {
   pdl_launch_dependents();
   pdl_wait();
   const int C = 64, tpr = 8;
@@ -397,14 +397,17 @@ __global__ void __launch_bounds__(256) stem_bn_relu_pool_kernel(const __nv_bfloa
     flip[j] = (scale[2 * j] < 0.f ? 0x00008000u : 0u) | (scale[2 * j + 1] < 0.f ? 0x80000000u : 0u);
   const uint32_t kNegInf = 0xFF80FF80u;
   const int Ho = H / 2, Wo = W / 2;
-  // one block iteration = one output row (n, ho); 32 pixel lanes x 8 channel groups walk it (no div/mod inside)
-  for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
-    const int n = row / Ho, ho = row - n * Ho;
-    const bool top = ho == 0;  // input row 2ho - 1 is padding (2ho + 1 <= H - 1 always: H is even)
-    const __nv_bfloat16* img = y + ((size_t)n * H + (top ? 0 : 2 * ho - 1)) * W * C + c0;
-    const size_t rstep1 = top ? 0 : (size_t)W * C;  // rows 0 and 1 of the window coincide (clamped) on the top edge
+  // output pixels as one flat range over the grid, 32 pixel lanes x 8 channel groups per block (a whole output row
+  // per block iteration left 12 % of the lanes idle at Wo = 56 and whole blocks idle at the end)
+  const int items = N * Ho * Wo;
+  {
 #pragma unroll 2
-    for (int wo = roff; wo < Wo; wo += 32) {
+    for (int q = blockIdx.x * 32 + roff; q < items; q += gridDim.x * 32) {
+      const int row = fd_div(fd_wo, q), wo = q - row * Wo;
+      const int n = fd_div(fd_ho, row), ho = row - n * Ho;
+      const bool top = ho == 0;  // input row 2ho - 1 is padding (2ho + 1 <= H - 1 always: H is even)
+      const __nv_bfloat16* img = y + ((size_t)n * H + (top ? 0 : 2 * ho - 1)) * W * C + c0;
+      const size_t rstep1 = top ? 0 : (size_t)W * C;  // rows 0 and 1 of the window coincide (clamped) on the top edge
       const bool left = wo == 0;
       const __nv_bfloat16* p0 = img + (size_t)(left ? 0 : 2 * wo - 1) * C;
       const size_t cstep1 = left ? 0 : (size_t)C;
@@ -474,15 +477,88 @@ __device__ __forceinline__ void pool_bwd_accumulate(const bf16x8& dp, uint2 widx
   }
 }
 
-__global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool,
-                                                            const uint8_t* __restrict__ idx,
-                                                            const __nv_bfloat16* __restrict__ y,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta,
-                                                            __nv_bfloat16* __restrict__ g_out, double* scratch, int N,
-                                                            int H, int W) {
+// One work item = one pixel pair (2j, 2j + 1) of one input row, 8 channels per thread.  Items are dealt to the grid
+// as one flat range and every thread keeps TWO of them in flight (all loads of both are issued before either is
+// consumed): with one row per block iteration the kernel was bound by the latency of its two dependent memory round
+// trips per row (ncu: 42 % of the stall samples on the first use of a load at 23 % occupancy, 13 % at the exit of
+// blocks whose rows ran out early).
+struct PoolBwdItem {
+  bf16x8 y0, y1, dpa, dpc, dqa, dqc;
+  uint2 ia, ic, ja, jc;
+  size_t o;
+  uint32_t krow_a;
+  bool live, has_b, has_c;
+};
+
+__device__ __forceinline__ void pool_bwd_load(PoolBwdItem& t, int q, int items, const __nv_bfloat16* __restrict__ dpool,
+                                              const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ y,
+                                              int H, int W, FastDiv fd_wo, FastDiv fd_h, int c0) {
+  const int C = 64, Ho = H / 2, Wo = W / 2;
+  t.live = q < items;
+  if (!t.live) return;
+  const int row = fd_div(fd_wo, q), j = q - row * Wo;
+  const int n = fd_div(fd_h, row), h = row - n * H;
+  // windows (ho, wo) with 2ho-1 <= h <= 2ho+1: ho in {h>>1, (h+1)>>1}; odd rows belong to two window rows (if the
+  // second one exists), and h is then the top tap (kernel row 0) of window row ho_b
+  const int ho_a = h >> 1, ho_b = (h + 1) >> 1;
+  t.has_b = (h & 1) && ho_b < Ho;
+  t.has_c = j + 1 < Wo;
+  t.krow_a = (uint32_t)(h - (2 * ho_a - 1)) * 3u;
+  t.o = ((size_t)row * W + 2 * j) * C + c0;
+  t.y0 = ld8(y + t.o), t.y1 = ld8(y + t.o + C);
+  const size_t pa0 = (((size_t)n * Ho + ho_a) * Wo + j) * C + c0, pa1 = pa0 + (t.has_c ? C : 0);
+  t.dpa = ld8_cached(dpool + pa0), t.dpc = ld8_cached(dpool + pa1);
+  t.ia = *reinterpret_cast<const uint2*>(idx + pa0), t.ic = *reinterpret_cast<const uint2*>(idx + pa1);
+  if (t.has_b) {
+    const size_t pb0 = (((size_t)n * Ho + ho_b) * Wo + j) * C + c0, pb1 = pb0 + (t.has_c ? C : 0);
+    t.dqa = ld8_cached(dpool + pb0), t.dqc = ld8_cached(dpool + pb1);
+    t.ja = *reinterpret_cast<const uint2*>(idx + pb0), t.jc = *reinterpret_cast<const uint2*>(idx + pb1);
+  }
+}
+
+__device__ __forceinline__ void pool_bwd_finish(const PoolBwdItem& t, const float (&scale)[8], const float (&shift)[8],
+                                                float (&s)[8], float (&d)[8], __nv_bfloat16* __restrict__ g_out) {
+  if (!t.live) return;
+  float g0[8], g1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g0[i] = g1[i] = 0.f;
+  pool_bwd_accumulate(t.dpa, t.ia, t.krow_a + 1u, g0);               // even pixel: middle tap of column j
+  pool_bwd_accumulate(t.dpa, t.ia, t.krow_a + 2u, g1);               // odd pixel: right tap of column j
+  pool_bwd_accumulate(t.dpc, t.ic, t.has_c ? t.krow_a : 0xFFu, g1);  // odd pixel: left tap of column j + 1
+  if (t.has_b) {
+    pool_bwd_accumulate(t.dqa, t.ja, 1u, g0);
+    pool_bwd_accumulate(t.dqa, t.ja, 2u, g1);
+    pool_bwd_accumulate(t.dqc, t.jc, t.has_c ? 0u : 0xFFu, g1);
+  }
+  const int C = 64;
+  float yv[8];
+  unpack8(t.y0, yv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    g0[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g0[i] : 0.f;
+    s[i] += g0[i];
+    d[i] = fmaf(g0[i], yv[i], d[i]);
+  }
+  st8(g_out + t.o, pack8(g0));
+  unpack8(t.y1, yv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    g1[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g1[i] : 0.f;
+    s[i] += g1[i];
+    d[i] = fmaf(g1[i], yv[i], d[i]);
+  }
+  st8(g_out + t.o + C, pack8(g1));
+}
+
+__global__ void __launch_bounds__(256, 2) stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dpool,
+                                                               const uint8_t* __restrict__ idx,
+                                                               const __nv_bfloat16* __restrict__ y,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ g_out, double* scratch, int N,
+                                                               int H, int W, FastDiv fd_wo, FastDiv fd_h) {
   __shared__ float red[2][256][9];
   pdl_launch_dependents();
   pdl_wait();
@@ -496,55 +572,14 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const __nv_bfloat16*
     shift[i] = beta[c0 + i] - mean[c0 + i] * scale[i];
     s[i] = d[i] = 0.f;
   }
-  const int Ho = H / 2, Wo = W / 2;
-  // one block iteration = one input row (n, h); windows (ho, wo) with 2ho-1 <= h <= 2ho+1: ho in {h>>1, (h+1)>>1}
-  for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
-    const int n = row / H, h = row - n * H;
-    const int ho_a = h >> 1, ho_b = (h + 1) >> 1;
-    const bool has_b = (h & 1) && ho_b < Ho;  // odd rows belong to two window rows (if the second one exists)
-    const uint32_t krow_a = (uint32_t)(h - (2 * ho_a - 1)) * 3u, krow_b = 0u;  // h is the top tap of window row ho_b
-    const size_t pool_a = ((size_t)n * Ho + ho_a) * Wo, pool_b = ((size_t)n * Ho + ho_b) * Wo;
-    for (int j = roff; j < Wo; j += 32) {  // pixel pair (2j, 2j + 1); window columns j and j + 1
-      const size_t o = ((size_t)row * W + 2 * j) * C + c0;
-      const bf16x8 y0 = ld8(y + o), y1 = ld8(y + o + C);
-      const bool has_c = j + 1 < Wo;
-      const size_t pa0 = (pool_a + j) * C + c0, pa1 = pa0 + (has_c ? C : 0);
-      float g0[8], g1[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g0[i] = g1[i] = 0.f;
-      {
-        const bf16x8 dpa = ld8_cached(dpool + pa0), dpc = ld8_cached(dpool + pa1);
-        const uint2 ia = *reinterpret_cast<const uint2*>(idx + pa0), ic = *reinterpret_cast<const uint2*>(idx + pa1);
-        pool_bwd_accumulate(dpa, ia, krow_a + 1u, g0);                    // even pixel: middle tap of column j
-        pool_bwd_accumulate(dpa, ia, krow_a + 2u, g1);                    // odd pixel: right tap of column j
-        pool_bwd_accumulate(dpc, ic, has_c ? krow_a : 0xFFu, g1);         // odd pixel: left tap of column j + 1
-      }
-      if (has_b) {
-        const size_t pb0 = (pool_b + j) * C + c0, pb1 = pb0 + (has_c ? C : 0);
-        const bf16x8 dpa = ld8_cached(dpool + pb0), dpc = ld8_cached(dpool + pb1);
-        const uint2 ia = *reinterpret_cast<const uint2*>(idx + pb0), ic = *reinterpret_cast<const uint2*>(idx + pb1);
-        pool_bwd_accumulate(dpa, ia, krow_b + 1u, g0);
-        pool_bwd_accumulate(dpa, ia, krow_b + 2u, g1);
-        pool_bwd_accumulate(dpc, ic, has_c ? krow_b : 0xFFu, g1);
-      }
-      float yv[8];
-      unpack8(y0, yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        g0[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g0[i] : 0.f;
-        s[i] += g0[i];
-        d[i] = fmaf(g0[i], yv[i], d[i]);
-      }
-      st8(g_out + o, pack8(g0));
-      unpack8(y1, yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        g1[i] = fmaf(yv[i], scale[i], shift[i]) > 0.f ? g1[i] : 0.f;
-        s[i] += g1[i];
-        d[i] = fmaf(g1[i], yv[i], d[i]);
-      }
-      st8(g_out + o + C, pack8(g1));
-    }
+  const int items = N * H * (W / 2);
+  const int stride = gridDim.x * 32;
+  for (int q = blockIdx.x * 32 + roff; q < items; q += 2 * stride) {
+    PoolBwdItem t0, t1;
+    pool_bwd_load(t0, q, items, dpool, idx, y, H, W, fd_wo, fd_h, c0);
+    pool_bwd_load(t1, q + stride, items, dpool, idx, y, H, W, fd_wo, fd_h, c0);
+    pool_bwd_finish(t0, scale, shift, s, d, g_out);
+    pool_bwd_finish(t1, scale, shift, s, d, g_out);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[0][threadIdx.x][i] = s[i], red[1][threadIdx.x][i] = d[i];
@@ -738,9 +773,10 @@ extern "C" int peclr_stem_bn_relu_pool(const void* y, const double* sum, const d
                                        float* invstd_out, float* running_mean, float* running_var, int N, int H,
                                        int W, float eps, float momentum, void* stream) {
   if ((H & 1) || (W & 1)) return -1001;
-  launch_pdl(stem_bn_relu_pool_kernel, grid_for((long long)N * (H / 2), 1, 4), 256, 0, (cudaStream_t)stream,
+  if ((long long)N * (H / 2) * (W / 2) >= (1ll << 30)) return -1001;
+  launch_pdl(stem_bn_relu_pool_kernel, grid_for((long long)N * (H / 2) * (W / 2), 32, 3), 256, 0, (cudaStream_t)stream,
              (const bf16*)y, sum, sumsq, gamma, beta, (bf16*)out, (uint8_t*)idx_out, mean_out, invstd_out, running_mean,
-             running_var, N, H, W, eps, momentum);
+             running_var, N, H, W, eps, momentum, make_fastdiv(W / 2), make_fastdiv(H / 2));
   return last_error();
 }
 
@@ -750,9 +786,10 @@ extern "C" int peclr_stem_pool_bwd(const void* dpool, const void* idx, const voi
   if ((H & 1) || (W & 1) || !idx) return -1001;
   cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * 64 * sizeof(double), (cudaStream_t)stream);
   if (e != cudaSuccess) return -(int)e;
-  launch_pdl(stem_pool_bwd_kernel, grid_for((long long)N * H, 1, 4), 256, 0, (cudaStream_t)stream,
+  if ((long long)N * H * (W / 2) >= (1ll << 30)) return -1001;
+  launch_pdl(stem_pool_bwd_kernel, grid_for((long long)N * H * (W / 2), 64, 2), 256, 0, (cudaStream_t)stream,
              (const bf16*)dpool, (const uint8_t*)idx, (const bf16*)y, mean, invstd, gamma, beta, (bf16*)g_out, scratch,
-             N, H, W);
+             N, H, W, make_fastdiv(W / 2), make_fastdiv(H));
   return last_error();
 }
 

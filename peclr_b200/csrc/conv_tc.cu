@@ -35,28 +35,6 @@ namespace peclr {
 
 constexpr int kStageA = 128 * 128;  // 128 pixel rows x 64 bf16
 
-// Division by a launch constant as multiply-high + shift (exact for 0 <= x < 2^31): the tile -> (w, h, n) arithmetic
-// sits at the head of every tile's critical path in all three warp roles, and a hardware integer division is a
-// ~25-instruction dependent chain through the reciprocal unit.
-struct FastDiv {
-  uint32_t mul, shr;
-  int d;
-};
-static FastDiv make_fastdiv(int d) {
-  FastDiv f{0u, 0u, d};
-  if (d > 1) {
-    int lg = 31 - __builtin_clz((unsigned)d);
-    if (d & (d - 1)) ++lg;  // ceil(log2 d)
-    const int sh = 31 + lg;
-    f.mul = (uint32_t)(((1ull << sh) + (unsigned)d - 1) / (unsigned)d);
-    f.shr = (uint32_t)(sh - 32);
-  }
-  return f;
-}
-__device__ __forceinline__ int fd_div(const FastDiv& f, int x) {
-  return f.d == 1 ? x : (int)(__umulhi((uint32_t)x, f.mul) >> f.shr);
-}
-
 struct GemmParams {
   CUtensorMap a_maps[kMaxViews];
   CUtensorMap b_map;

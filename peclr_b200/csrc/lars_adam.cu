@@ -65,13 +65,42 @@ __global__ void __launch_bounds__(256) opt_update_kernel(const OptArgs a) {
   } else {
     wd_eff = wd;  // plain Adam: L2 weight decay folded into the gradient
   }
-  for (long long i = b + threadIdx.x; i < e; i += 256) {
-    float pv = a.p[i];
-    const float gv = (a.g[i] + wd_eff * pv) * trust;
-    const float mv = a.beta1 * a.m[i] + (1.f - a.beta1) * gv;
-    const float vv = a.beta2 * a.v[i] + (1.f - a.beta2) * gv * gv;
+  // one element: the same arithmetic in the vector body and the scalar tail (bit-identical either way)
+  auto update = [&](float& pv, float gin, float& mv, float& vv) {
+    const float gv = (gin + wd_eff * pv) * trust;
+    mv = a.beta1 * mv + (1.f - a.beta1) * gv;
+    vv = a.beta2 * vv + (1.f - a.beta2) * gv * gv;
     const float denom = sqrtf(vv) / a.bc2_sqrt + a.adam_eps;
     pv -= a.step_size * (mv / denom);
+  };
+  long long i0 = b;
+  if ((b & 3) == 0) {  // 16-byte body: four streams x 16 B per thread and iteration (the scalar loop left the kernel
+                       // latency bound at 4.4 TB/s: 70 % of its stall samples on the first use of a 4-byte load)
+    const long long n4 = (e - b) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(a.p + b);
+    const float4* g4 = reinterpret_cast<const float4*>(a.g + b);
+    float4* m4 = reinterpret_cast<float4*>(a.m + b);
+    float4* v4 = reinterpret_cast<float4*>(a.v + b);
+#pragma unroll 2
+    for (long long i = threadIdx.x; i < n4; i += 256) {
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      const float4 gv = g4[i];
+      update(pv.x, gv.x, mv.x, vv.x);
+      update(pv.y, gv.y, mv.y, vv.y);
+      update(pv.z, gv.z, mv.z, vv.z);
+      update(pv.w, gv.w, mv.w, vv.w);
+      p4[i] = pv, m4[i] = mv, v4[i] = vv;
+      if (a.p_bf16) {
+        uint2 o;
+        o.x = pack_bf16x2(pv.x, pv.y), o.y = pack_bf16x2(pv.z, pv.w);
+        *reinterpret_cast<uint2*>(a.p_bf16 + b + 4 * i) = o;
+      }
+    }
+    i0 = b + 4 * n4;
+  }
+  for (long long i = i0 + threadIdx.x; i < e; i += 256) {
+    float pv = a.p[i], mv = a.m[i], vv = a.v[i];
+    update(pv, a.g[i], mv, vv);
     a.p[i] = pv;
     a.m[i] = mv;
     a.v[i] = vv;
