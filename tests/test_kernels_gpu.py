@@ -61,6 +61,10 @@ A2_CASES = [
     (4, 7, 7, 512, 2048, 1, 1), (4, 14, 14, 1024, 2048, 1, 2), (4, 7, 7, 2048, 512, 1, 1), (4, 7, 7, 512, 512, 3, 1),
 ]
 ALL_CONV_CASES = CONV_CASES + A2_CASES
+# many pixels, small weight gradient: ~100 pixel splits whose ordered reduction shares each element among 2..16 thread
+# rows (wgrad_reduce_split_kernel) -- the layer-1 / layer-2 shapes at (close to) the training batch
+WGRAD_SPLIT_CASES = [(48, 56, 56, 64, 256, 1, 1), (48, 56, 56, 64, 64, 3, 1), (64, 28, 28, 128, 512, 1, 1),
+                     (40, 56, 56, 256, 64, 1, 1)]
 
 
 def _conv_data(case, seed=0):
@@ -109,7 +113,7 @@ def test_conv_dgrad(ops, case):
     assert rel_l2(acc.float(), want) < 1.5e-2
 
 
-@pytest.mark.parametrize("case", ALL_CONV_CASES)
+@pytest.mark.parametrize("case", ALL_CONV_CASES + WGRAD_SPLIT_CASES)
 def test_conv_wgrad(ops, case):
     n, h, w, cin, cout, k, s = case
     x, wt = _conv_data(case, 3)
