@@ -321,6 +321,8 @@ def measure(ctx, model_size, batch, size, accumulate, steps, warmup, sample_cloc
                     if f_train else None}
             try:  # (explanatory extra: never let it take the bench line down)
                 roof["per_launch_roofline"] = launch_bound_fraction(prof, pk["tf_sustained"], pk["hbm"])
+                if os.environ.get("PECLR_BENCH_DUMP_LAUNCHES"):
+                    dump_launch_table(prof, pk["tf_sustained"], pk["hbm"], os.environ["PECLR_BENCH_DUMP_LAUNCHES"])
             except Exception as exc:  # pragma: no cover
                 roof["per_launch_roofline"] = {"error": repr(exc)}
     res = {"value": round(value, 1), "ms_per_step": round(ms / steps, 3), "steps": steps, "warmup": warmup,
@@ -564,6 +566,28 @@ def launch_bound_fraction(prof, peak_tflops, peak_gbs):
         return None
     return {"bound_ms": round(bound, 3), "measured_ms": round(meas, 3), "frac": round(bound / meas, 4),
             "launches": n_all, "hbm_bound_launches": n_hbm}
+
+
+def dump_launch_table(prof, peak_tflops, peak_gbs, path):
+    """Per conv shape (C-ABI call + geometry): launches, mean CUDA-event time, achieved TFLOP/s and algorithmic GB/s,
+    and the fraction of that launch's own roofline max(FLOPs / tensor peak, bytes / HBM peak) -- the table the tuning
+    decisions are read from (PECLR_BENCH_DUMP_LAUNCHES=<file>)."""
+    import collections
+
+    rows = collections.OrderedDict()
+    for name, a, ms_k in prof:
+        geo = tuple(a[3:6]) if name.startswith("peclr_stem") else tuple(a[3:8 if "finish" in name else 10])
+        r = rows.setdefault((name.replace("peclr_", ""), geo), [0, 0.0, conv_flops(name, a), conv_bytes(name, a)])
+        r[0] += 1
+        r[1] += ms_k
+    with open(path, "w") as f:
+        f.write("%-22s %-34s %3s %9s %8s %8s %6s\n" % ("call", "N,H,W,Cin,Cout[,k,s]", "n", "us/launch", "TFLOP/s",
+                                                       "GB/s", "frac"))
+        for (name, geo), (n, ms_sum, fl, by) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            t = ms_sum / n * 1e-3
+            bound = max(fl / (peak_tflops * 1e12), by / (peak_gbs * 1e9))
+            f.write("%-22s %-34s %3d %9.1f %8.0f %8.0f %6.2f\n" % (name, ",".join(map(str, geo)), n, t * 1e6,
+                                                                   fl / t / 1e12, by / t / 1e9, bound / t))
 
 
 def conv_flops(name, a):

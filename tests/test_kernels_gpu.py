@@ -398,7 +398,9 @@ def test_weight_transpose_and_cast(ops):
 
 
 @pytest.mark.parametrize("case", [(4, 8, 8, 64, 256, 1, 1), (2, 14, 14, 128, 128, 3, 1), (4, 16, 16, 128, 128, 3, 2),
-                                  (32, 14, 14, 256, 256, 3, 1), (3, 8, 8, 512, 128, 1, 1)])
+                                  (32, 14, 14, 256, 256, 3, 1), (3, 8, 8, 512, 128, 1, 1),
+                                  # >= 1024 gradient channels: single statistics copy + exchange buffer
+                                  (4, 14, 14, 1024, 256, 1, 1), (6, 7, 7, 2048, 512, 1, 1)])
 def test_dgrad_with_fused_bn_reduce(ops, case):
     """The dgrad epilogue's fused BatchNorm-backward sums equal the separate reduce pass on the same dx."""
     from peclr_b200 import _lib
