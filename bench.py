@@ -539,7 +539,10 @@ def conv_bytes(name, a):
         return 2.0 * (n * h * w * (3 * cin + cout) + cin * cout) + n * h * w * cin / 8.0
     n, h, w, cin, cout, k, s = a[3:10]
     big, small = n * h * w * cin, n * (h // s) * (w // s) * cout  # input-side / output-side activation elements
-    total = big + small + cout * k * k * cin
+    # a strided 1x1 convolution only touches the sampled input pixels (fprop / wgrad read them; the dgrad still
+    # writes the whole, mostly zero, gradient tensor)
+    sampled = big // (s * s) if (k == 1 and s > 1 and "dgrad" not in name) else big
+    total = sampled + small + cout * k * k * cin
     if name == "peclr_conv2d_dgrad" and a[10]:
         total += big
     if name == "peclr_conv2d_dgrad_bnreduce":

@@ -220,6 +220,8 @@ def test_bench_roofline_arithmetic():
     # the whole ResNet-50 @ 224 figure of SURVEY 8(d) is 24.287 GFLOP per image: one 3x3 256->256 @14x14 is 0.2312 of it
     c3 = ("peclr_conv2d_fprop", (0, 0, 0, 1, 14, 14, 256, 256, 3, 1, 0, 0, 0))
     assert abs(bench.conv_flops(*c3) / 1e6 - 2 * 115.6) < 0.1  # table A2: 115.6 MMAC per image
+    ds = ("peclr_conv2d_fprop", (0, 0, 0, 256, 56, 56, 256, 512, 1, 2))  # strided 1x1: only the sampled pixels are read
+    assert bench.conv_bytes(*ds) == 2.0 * (256 * 28 * 28 * (256 + 512) + 512 * 256)
     rec = [fprop + (0.10,), acc + (0.16,), ("peclr_conv2d_wgrad", (0,) * 11, 0.5)]
     out = bench.launch_bound_fraction(rec, 1362.3, 6540.8)
     assert out["launches"] == 2 and out["hbm_bound_launches"] == 2 and 0 < out["frac"] < 1
