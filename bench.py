@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 # conv-only training FLOPs per image, 2*(3*MAC_fwd - MAC_conv1)
 F_TRAIN = {("50", 224): 24.287e9, ("152", 224): 68.834e9, ("50", 64): 1.983e9, ("50", 128): 7.930e9}
 CONV_CALLS = {"peclr_conv2d_fprop", "peclr_conv2d_dgrad", "peclr_conv2d_dgrad_bnreduce", "peclr_conv2d_dgrad_finish",
+              "peclr_conv2d_dgrad_finish_lattice",
               "peclr_conv2d_wgrad", "peclr_conv2d_wgrad_partials", "peclr_stem_fprop", "peclr_stem_wgrad"}
 CPU_SAMPLE_PAIRS = 32  # per-step sample of BOTH CPU legs (cpu_baseline and --impl reference), scaled per image
 
@@ -552,16 +553,16 @@ def conv_bytes(name, a):
     if name.startswith("peclr_stem"):
         n, h, w = a[3], a[4], a[5]
         return 2.0 * (n * (h // 2 + 3) * (w // 2 + 4) * 16 + n * (h // 2) * (w // 2) * 64 + 64 * 4 * 64)
-    if name == "peclr_conv2d_dgrad_finish":  # (1x1 / stride 1): dy + weights + dx read-modify-write + y + mask bits
-        n, h, w, cin, cout = a[3:8]
+    if name.startswith("peclr_conv2d_dgrad_finish"):  # (1x1 / stride 1): dy + weights + dx read-modify-write + y + mask
+        n, h, w, cin, cout = a[3:8]  # (the lattice form reads a quarter of dx as data; counted as the whole tensor)
         return 2.0 * (n * h * w * (3 * cin + cout) + cin * cout) + n * h * w * cin / 8.0
     n, h, w, cin, cout, k, s = a[3:10]
     big, small = n * h * w * cin, n * (h // s) * (w // s) * cout  # input-side / output-side activation elements
     # a strided 1x1 convolution only touches the sampled input pixels (fprop / wgrad read them; the dgrad still
     # writes the whole, mostly zero, gradient tensor)
-    sampled = big // (s * s) if (k == 1 and s > 1 and "dgrad" not in name) else big
+    sampled = big // (s * s) if (k == 1 and s > 1 and ("dgrad" not in name or a[10] == 2)) else big
     total = sampled + small + cout * k * k * cin
-    if name == "peclr_conv2d_dgrad" and a[10]:
+    if name == "peclr_conv2d_dgrad" and a[10] == 1:
         total += big
     if name == "peclr_conv2d_dgrad_bnreduce":
         total += big
@@ -616,7 +617,7 @@ def conv_flops(name, a):
     if name.startswith("peclr_stem"):
         n, h, w = a[3], a[4], a[5]
         return 2.0 * n * (h // 2) * (w // 2) * 64 * 147
-    if name == "peclr_conv2d_dgrad_finish":
+    if name.startswith("peclr_conv2d_dgrad_finish"):
         n, h, w, cin, cout = a[3:8]
         return 2.0 * n * h * w * cout * cin
     n, h, w, cin, cout, k, s = a[3:10]

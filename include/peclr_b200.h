@@ -44,7 +44,9 @@ int peclr_abi_version(void);
 int peclr_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, double* stat_sum, double* stat_sumsq, void* stream);
 /* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,H/s,W/s,Cout], wt[Cin][k*k][Cout]); wt is the transposed
- * weight copy produced by peclr_weight_transpose.  accumulate != 0 adds into dx (TMA reduce-add). */
+ * weight copy produced by peclr_weight_transpose.  accumulate = 1 adds into dx (TMA reduce-add); accumulate = 2
+ * (k = 1, stride = 2 only): scatter to the sampled pixels without zero-filling the others -- for
+ * peclr_conv2d_dgrad_finish_lattice, which never reads them as data. */
 int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int accumulate, void* stream);
 /* The same dgrad with the BatchNorm-backward reduction of the BN + ReLU sitting in front of this convolution fused
@@ -64,6 +66,13 @@ int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N,
  * for that block output; follow with peclr_bn_bwd_apply(mask_mode 0) on dx.  Cin multiple of 128. */
 int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
                               const void* bn_y, const void* mask_bits, double* scratch, void* stream);
+/* The same with acc_stride = 2 for the first block of a stage, where the gradient gathered so far is the down-sampling
+ * shortcut's (torchvision Bottleneck.downsample: conv1x1 stride 2): written by peclr_conv2d_dgrad(k = 1, stride = 2,
+ * accumulate = 2) = scatter to the pixels with even row and even column WITHOUT zero-filling the rest, which this call
+ * then reads as 0 (never as data).  acc_stride = 1 is peclr_conv2d_dgrad_finish.  H, W even. */
+int peclr_conv2d_dgrad_finish_lattice(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                                      const void* bn_y, const void* mask_bits, double* scratch, int acc_stride,
+                                      void* stream);
 /* dw[Cout][k*k][Cin] (fp32) += dy^T * im2col(x).  The pixel dimension is split over thread blocks; the splits'
  * partial products go to `workspace` (peclr_conv2d_wgrad_workspace_bytes for the same geometry; may be NULL when
  * that is 0) and a second kernel adds them to dw in a fixed order. */

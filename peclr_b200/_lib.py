@@ -24,6 +24,7 @@ SIGNATURES = {
     "peclr_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, P],
     "peclr_conv2d_dgrad_bnreduce": [P, P, P, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "peclr_conv2d_dgrad_finish": [P, P, P, I, I, I, I, I, P, P, P, P],
+    "peclr_conv2d_dgrad_finish_lattice": [P, P, P, I, I, I, I, I, P, P, P, I, P],
     "peclr_conv2d_wgrad_workspace_bytes": [I, I, I, I, I, I, I],
     "peclr_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, P, L, P],
     "peclr_conv2d_wgrad_splits": [I, I, I, I, I, I, I],

@@ -107,6 +107,7 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
                       const float* bn_gamma, const float* bn_beta, double* scratch, cudaStream_t st) {
   if (Cin % 64 || Cout % 64 || (k != 1 && k != 3)) return PECLR_ERR_ARG;
   if (bn_y && (accumulate || !scratch || Cin > 2048)) return PECLR_ERR_ARG;
+  if (accumulate < 0 || accumulate > 2 || (accumulate == 2 && !(k == 1 && stride == 2))) return PECLR_ERR_ARG;
   const int Ho = H / stride, Wo = W / stride;
   TapTable taps;
   memset(&taps, 0, sizeof(taps));
@@ -154,8 +155,11 @@ static int dgrad_impl(const void* dy, const void* wt, void* dx, int N, int H, in
   a = nhwc_view(dy, N, Ho, Wo, Cout);
   if (k == 1) {
     if (bn_y) return PECLR_ERR_ARG;  // (3/4 of dx is plain zero here; no caller needs the fusion)
-    // only the even/even pixels of dx receive gradient
-    if (!accumulate) {
+    // only the even/even pixels of dx receive gradient; accumulate == 2: plain scatter, the caller promises that
+    // the other pixels are never read as they are (peclr_conv2d_dgrad_finish_lattice)
+    if (accumulate == 2) {
+      accumulate = 0;
+    } else if (!accumulate) {
       cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, st);
       if (e != cudaSuccess) return -(int)e;
     }
@@ -195,10 +199,11 @@ extern "C" int peclr_conv2d_dgrad(const void* dy, const void* wt, void* dx, int 
 // dx holds the gradient gathered so far (shortcut branch, or the down-sampling branch's dgrad) and receives
 // (dx + dgrad(dy)) * relu'(previous block's output), the mask coming from the bits bn_apply wrote; scratch[0:Cin] =
 // sum g, scratch[Cin:2Cin] = sum g*y for the BatchNorm in front of that ReLU (bn_y = its input).
-extern "C" int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
-                                         int Cout, const void* bn_y, const void* mask_bits, double* scratch,
-                                         void* stream) {
+static int dgrad_finish_impl(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin, int Cout,
+                             const void* bn_y, const void* mask_bits, double* scratch, int acc_stride, void* stream) {
   if (!dy || !wt || !dx || !bn_y || !mask_bits || !scratch) return PECLR_ERR_ARG;
+  if (acc_stride != 1 && (acc_stride != 2 || (H & 1) || (W & 1) || (int64_t)N * H * W >= (1ll << 31)))
+    return PECLR_ERR_ARG;
   if (Cin % 128 || Cout % 64 || Cin > 2048) return PECLR_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)2 * Cin * sizeof(double), st);
@@ -213,7 +218,23 @@ extern "C" int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* d
   br.mean = br.invstd = br.gamma = br.beta = nullptr;
   br.mask_bits = static_cast<const uint8_t*>(mask_bits);
   br.pix_base = 0, br.pix_w = 1, br.pix_h = 0, br.pix_n = 0;
+  br.acc_stride = acc_stride, br.img_w = W;
   return conv_gemm_launch(&a, 1, wt, Cout, Cin, d, taps, 1, Cout / 64, scratch, scratch + Cin, 0, st, &br);
+}
+
+extern "C" int peclr_conv2d_dgrad_finish(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,
+                                         int Cout, const void* bn_y, const void* mask_bits, double* scratch,
+                                         void* stream) {
+  return dgrad_finish_impl(dy, wt, dx, N, H, W, Cin, Cout, bn_y, mask_bits, scratch, 1, stream);
+}
+
+// The same when the gradient gathered so far is the scatter of a stride-2 1x1 dgrad (the down-sampling shortcut of a
+// stage's first block, peclr_conv2d_dgrad with accumulate = 2: no zero fill): only the pixels with even row and even
+// column of dx are read, the rest counts as 0 -- the 100-400 MB memset of dx and its re-read disappear.
+extern "C" int peclr_conv2d_dgrad_finish_lattice(const void* dy, const void* wt, void* dx, int N, int H, int W,
+                                                 int Cin, int Cout, const void* bn_y, const void* mask_bits,
+                                                 double* scratch, int acc_stride, void* stream) {
+  return dgrad_finish_impl(dy, wt, dx, N, H, W, Cin, Cout, bn_y, mask_bits, scratch, acc_stride, stream);
 }
 
 extern "C" int peclr_conv2d_dgrad_bnreduce(const void* dy, const void* wt, void* dx, int N, int H, int W, int Cin,

@@ -66,6 +66,8 @@ struct GemmParams {
   const uint8_t* mask_bits;
   long long pix_base, pix_w, pix_h, pix_n;  // pixel index of view element (w, h, n) = base + w*pix_w + h*pix_h + n*pix_n
   int mask_row_bytes;
+  int acc_stride;      // 2: the tile already in the tensor is valid on the even-row / even-column pixel lattice only
+  FastDiv fd_img_w;    // (image width, for the row parity of a flat pixel index)
   // filter-row halo mode (HALO kernels): a tap table entry is a GROUP of halo_taps taps that differ only in dh
   // (dh = taps.dh[g] + t).  One (Hb + halo_taps - 1) x Wb input box per group and channel chunk serves all of them:
   // tap t reads the same shared-memory buffer from row t * Wb on (Wb is a multiple of 8, so that offset is a
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     // issued at the point of use, this global load was the largest single stall of the kernel (14 % of all samples),
     // and still 9 % when issued at the top of its own tile.
     const bool finish = p.bn_reduce == 2;
-    auto fetch_mask = [&](int t, uint32_t* words) {
+    auto fetch_mask = [&](int t, uint32_t* words, bool* acc_valid) {
       const int tq = fd_div(p.fd_n_tiles, t);
       const int nt = t - tq * p.n_tiles;
       const int mt = tq * CTAS + cta_rank;
@@ -300,8 +302,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       const int n = nq * p.Nb + (row >> p.log_wbhb);
       // off-image rows: the TMA store clips them, the statistics must not see them
       const bool on_image = t < total_tiles && w < p.d_w && h < p.d_h && n < p.d_n;
-      const long long mask_row =
-          (p.pix_base + (long long)w * p.pix_w + (long long)h * p.pix_h + (long long)n * p.pix_n) * p.mask_row_bytes;
+      const long long pidx = p.pix_base + (long long)w * p.pix_w + (long long)h * p.pix_h + (long long)n * p.pix_n;
+      const long long mask_row = pidx * p.mask_row_bytes;
+      // (image width even: the column parity of a flat pixel index is its own parity)
+      *acc_valid = p.acc_stride == 1 || (((int)pidx | fd_div(p.fd_img_w, (int)pidx)) & 1) == 0;
 #pragma unroll
       for (int ci = 0; ci < BN / 64; ++ci)
         words[ci] = on_image ? *reinterpret_cast<const uint32_t*>(p.mask_bits + mask_row +
@@ -309,7 +313,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                              : 0u;
     };
     uint32_t mask_next[BN / 64];
-    if (finish) fetch_mask(first_tile, mask_next);
+    bool acc_valid_next = true;
+    if (finish) fetch_mask(first_tile, mask_next, &acc_valid_next);
     int it = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
@@ -325,10 +330,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       uint8_t* sDt = sD + (p.d_bufs == 2 ? (it & 1) * kTileD : 0u);
       const uint32_t sD32 = smem_u32(sDt);
       uint32_t mask_word[BN / 64];
+      bool acc_valid = true;
       if (finish) {
 #pragma unroll
         for (int ci = 0; ci < BN / 64; ++ci) mask_word[ci] = mask_next[ci];
-        fetch_mask(t + tile_step, mask_next);
+        acc_valid = acc_valid_next;
+        fetch_mask(t + tile_step, mask_next, &acc_valid_next);
       }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
@@ -353,7 +360,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c16 = (chunk & 1) * 4 + j;
-            const uint4 g = lds_v4(box + gdelta + ((c16 ^ (row & 7)) << 4));
+            uint4 g = lds_v4(box + gdelta + ((c16 ^ (row & 7)) << 4));
+            if (!acc_valid) g = make_uint4(0u, 0u, 0u, 0u);  // never-written memory: selected away, not multiplied
             const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -1049,6 +1057,9 @@ int conv_gemm_launch(const View4* a_views, int num_views, const void* w, int64_t
       p.mask_bits = bnr->mask_bits;
       p.pix_base = bnr->pix_base, p.pix_w = bnr->pix_w, p.pix_h = bnr->pix_h, p.pix_n = bnr->pix_n;
       p.mask_row_bytes = (int)(nout / 8);
+      p.acc_stride = bnr->acc_stride;
+      p.fd_img_w = make_fastdiv(bnr->img_w > 0 ? bnr->img_w : 1);
+      if (p.acc_stride != 1 && (p.acc_stride != 2 || bnr->img_w < 2 || (bnr->img_w & 1))) return PECLR_ERR_ARG;
     }
   }
   const bool pairs = use_cta_pairs() && d_view.w * d_view.h * d_view.n > 128;  // at least two m tiles

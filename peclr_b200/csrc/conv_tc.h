@@ -62,6 +62,9 @@ struct BnReduce {
   // Pixel index of view element (w, h, n) = pix_base + w*pix_w + h*pix_h + n*pix_n.
   const uint8_t* mask_bits = nullptr;
   long long pix_base = 0, pix_w = 0, pix_h = 0, pix_n = 0;
+  // finish mode: 2 = only the pixels with even image row AND even image column of D_in_tensor hold a gradient (the
+  // scatter of a stride-2 1x1 dgrad into a buffer that was never zeroed); the rest is read as 0.  img_w = image width.
+  int acc_stride = 1, img_w = 0;
 };
 
 // D[pix, n] (+)= sum_taps sum_c A_view[pix + tap, c] * Wmat[n, koff(tap) + c]; optional column statistics.

@@ -47,6 +47,8 @@ class StepEngine:
         # block-output BatchNorm backward: the dgrad that completes a block input's gradient also masks it with the
         # previous block's ReLU bits and accumulates that block's BN-backward sums (peclr_conv2d_dgrad_finish)
         self.fuse_block_bn = os.environ.get("PECLR_FUSE_BLOCK_BN", "1") != "0"
+        # stride-2 shortcut dgrad scattered into an unzeroed buffer, read on its pixel lattice by the finishing dgrad
+        self.finish_lattice = os.environ.get("PECLR_FINISH_LATTICE", "1") != "0"
         # weight gradients, optional: every convolution of a ResNet stage writes its pixel-split slabs into its own
         # region of one workspace and ONE ordered reduction per stage adds them to the gradients (instead of one per
         # convolution).  Measured SLOWER on B200 (same box: ResNet-50 17.55 vs 17.28 ms, ResNet-152 39.67 vs 38.85 ms):
@@ -442,9 +444,14 @@ class StepEngine:
                 dyd = ops.bn_backward(g, None, yd, dsv, self._p(dbn, "weight"), self._g(dbn, "weight"),
                                       self._g(dbn, "bias"), scratch=scratch, dy=g)
                 wgrad(lambda a_in=a_in, dyd=dyd, dconv=dconv: conv_wgrad(dconv, a_in, dyd), a_in, dyd)
-                if finish:  # down-sampling branch first (its stride-2 form only touches a sub-lattice), conv1 finishes
-                    da = ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride)
-                    ops.conv2d_dgrad_finish(dy, self._wt(conv1), da, y_prev, prev["mask"], scratch)
+                if finish:  # down-sampling branch first, conv1 finishes.  Its stride-2 form only touches the even /
+                    # even pixel lattice: scattered into a buffer that is never zeroed, the finishing dgrad reads the
+                    # other pixels as 0 (no 100-400 MB memset, no re-read of it)
+                    lattice = self.finish_lattice and dconv.stride == 2 and dconv.k == 1
+                    da = ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride,
+                                          scatter_only=lattice)
+                    ops.conv2d_dgrad_finish(dy, self._wt(conv1), da, y_prev, prev["mask"], scratch,
+                                            acc_stride=2 if lattice else 1)
                 else:
                     da = ops.conv2d_dgrad(dy, self._wt(conv1), tuple(a_in.shape), conv1.k, conv1.stride)
                     ops.conv2d_dgrad(dyd, self._wt(dconv), tuple(a_in.shape), 1, dconv.stride, out=da, accumulate=True)

@@ -80,13 +80,16 @@ def conv2d_fprop(x, w, k, stride, want_stats=False, out=None, stats=None):
     return (y, stats) if want_stats else y
 
 
-def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False):
-    """dy [N,H/s,W/s,Cout], wt [Cin,k*k,Cout] -> dx [N,H,W,Cin]."""
+def conv2d_dgrad(dy, wt, in_shape, k, stride, out=None, accumulate=False, scatter_only=False):
+    """dy [N,H/s,W/s,Cout], wt [Cin,k*k,Cout] -> dx [N,H,W,Cin].  scatter_only (1x1 / stride 2): only the sampled
+    pixels of dx are written, the rest stays UNINITIALISED (for conv2d_dgrad_finish(..., acc_stride=2))."""
     _need_cuda(dy, wt)
     n, h, wd, cin = in_shape
     cout = dy.shape[-1]
     dx = out if out is not None else torch.empty(in_shape, dtype=bf16, device=dy.device)
-    _lib.call("peclr_conv2d_dgrad", dy, wt, dx, n, h, wd, cin, cout, k, stride, int(accumulate), _s())
+    assert not (scatter_only and accumulate)
+    _lib.call("peclr_conv2d_dgrad", dy, wt, dx, n, h, wd, cin, cout, k, stride, 2 if scatter_only else int(accumulate),
+              _s())
     return dx
 
 
@@ -103,16 +106,22 @@ def conv2d_dgrad_bnreduce(dy, wt, in_shape, k, stride, bn_y, saved, gamma, beta,
     return dx
 
 
-def conv2d_dgrad_finish(dy, wt, dx, bn_y, mask_bits, scratch):
+def conv2d_dgrad_finish(dy, wt, dx, bn_y, mask_bits, scratch, acc_stride=1):
     """1x1 / stride-1 dgrad completing a residual block's input gradient IN PLACE: dx <- (dx + dgrad(dy)) masked with
     the previous block output's ReLU bits; scratch (fp64 [2*Cin]) <- sum g, sum g*y for that block's last BatchNorm
-    (bn_y = its input).  Follow with bn_backward(dx, None, bn_y, ..., reduce_done=True)."""
+    (bn_y = its input).  Follow with bn_backward(dx, None, bn_y, ..., reduce_done=True).
+    acc_stride=2: dx holds a gradient on its even-row / even-column pixels only (conv2d_dgrad(..., scatter_only=True)
+    of a stride-2 1x1 convolution into a buffer that was never zeroed); every other pixel counts as 0."""
     _need_cuda(dy, wt, dx, bn_y, mask_bits)
     n, h, wd, cin = dx.shape
     cout = dy.shape[-1]
     assert scratch.dtype == f64 and scratch.numel() >= 2 * cin and mask_bits.dtype == torch.uint8
     assert tuple(bn_y.shape) == tuple(dx.shape) and mask_bits.numel() == n * h * wd * cin // 8
-    _lib.call("peclr_conv2d_dgrad_finish", dy, wt, dx, n, h, wd, cin, cout, bn_y, mask_bits, scratch, _s())
+    if acc_stride == 1:
+        _lib.call("peclr_conv2d_dgrad_finish", dy, wt, dx, n, h, wd, cin, cout, bn_y, mask_bits, scratch, _s())
+    else:
+        _lib.call("peclr_conv2d_dgrad_finish_lattice", dy, wt, dx, n, h, wd, cin, cout, bn_y, mask_bits, scratch,
+                  int(acc_stride), _s())
     return dx
 
 

@@ -539,3 +539,42 @@ def test_dgrad_finish(ops, case):
     torch.cuda.synchronize()
     assert torch.equal(dx2, dx) and torch.equal(scratch2, scratch)
     assert rel_l2(dx.float(), old.float() * keep) < 6e-3
+
+
+@pytest.mark.parametrize("case", [(2, 56, 56, 256, 64, 512), (3, 28, 28, 512, 128, 1024), (4, 14, 14, 1024, 256, 2048),
+                                  (3, 6, 10, 128, 64, 128)])
+def test_dgrad_finish_on_scattered_shortcut_gradient(ops, case):
+    """First block of a stage: the down-sampling shortcut's stride-2 dgrad is scattered to the even / even pixels of a
+    buffer that is NEVER zeroed (NaN-filled here), and the finishing dgrad reads every other pixel as 0.  Same result,
+    bit for bit, as zero-fill + scatter + the plain finishing dgrad."""
+    n, h, w, cin, cout, cds = case  # conv1: cin -> cout (stride 1); shortcut conv: cin -> cds (1x1, stride 2)
+    g = torch.Generator(device="cuda").manual_seed(41)
+    wt = (torch.randn(cout, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    wds = (torch.randn(cds, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    dy = nhwc(torch.randn(n, cout, h, w, device="cuda", generator=g).bfloat16())
+    dyd = nhwc(torch.randn(n, cds, h // 2, w // 2, device="cuda", generator=g).bfloat16())
+    y_prev = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    keep = torch.rand(n, h, w, cin, device="cuda", generator=g) > 0.4
+    bits = (keep.view(-1, cin // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(
+        -1, dtype=torch.uint8).contiguous()
+    wt_t = krsc(wt).permute(2, 1, 0).contiguous()
+    wds_t = krsc(wds).permute(2, 1, 0).contiguous()
+    # zero fill + scatter, plain finishing dgrad
+    a = ops.conv2d_dgrad(dyd, wds_t, (n, h, w, cin), 1, 2)
+    s_a = torch.empty(2 * cin, device="cuda", dtype=torch.float64)
+    ops.conv2d_dgrad_finish(dy, wt_t, a, y_prev, bits, s_a)
+    # scatter into NaNs, lattice form
+    b = torch.full((n, h, w, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv2d_dgrad(dyd, wds_t, (n, h, w, cin), 1, 2, out=b, scatter_only=True)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(b[:, 1::2].float()).all()) and bool(torch.isnan(b[:, :, 1::2].float()).all())
+    assert not bool(torch.isnan(b[:, ::2, ::2].float()).any())
+    s_b = torch.empty_like(s_a)
+    ops.conv2d_dgrad_finish(dy, wt_t, b, y_prev, bits, s_b, acc_stride=2)
+    torch.cuda.synchronize()
+    assert not bool(torch.isnan(b.float()).any())
+    assert torch.equal(a, b) and torch.equal(s_a, s_b)
+    # and against fp32 torch
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float(), dy.permute(0, 3, 1, 2).float()) + \
+        torch.nn.grad.conv2d_input((n, cin, h, w), wds.float(), dyd.permute(0, 3, 1, 2).float(), stride=2)
+    assert rel_l2(b.float(), nhwc(ref) * keep) < 1.2e-2
