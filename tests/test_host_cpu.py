@@ -377,3 +377,28 @@ def test_stage_ranges_partition_the_flat_gradient_buffer(model):
     assert ranges[-1] == (0, by_name["encoder.features.5.0.conv1.weight"].begin)
     model.enable_overlapped_sync(True)  # one process: stays off
     assert model._after_stage_hook is None
+
+
+def test_build_digest_covers_sources_only(tmp_path, monkeypatch):
+    """The build stamp keys bench.py's `roofline.traffic` to the kernel sources: objects, the library and the stamp
+    itself must not change it (it used to, so every rebuild invalidated the committed ncu capture)."""
+    from peclr_b200 import build
+
+    before = build._digest()
+    junk = [os.path.join(build.CSRC, n) for n in ("zz_test_object.o", ".zz_test_stamp")]
+    try:
+        for j in junk:
+            with open(j, "w") as f:
+                f.write("not a source")
+        assert build._digest() == before
+    finally:
+        for j in junk:
+            if os.path.exists(j):
+                os.remove(j)
+    probe = os.path.join(build.CSRC, "zz_test_probe.cuh")
+    try:
+        with open(probe, "w") as f:
+            f.write("// a source file does count\n")
+        assert build._digest() != before
+    finally:
+        os.remove(probe)
